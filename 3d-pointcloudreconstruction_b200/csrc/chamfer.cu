@@ -1,0 +1,444 @@
+// chamfer.cu -- B200-native Chamfer nearest-neighbour forward and gradient scatter.
+//
+// Replaces metric/chamfer3D/chamfer3D.cu of the reference (NmDistanceKernel :12-134,
+// NmDistanceGradKernel :155-174 and their launchers :136-154, :176-195).  Results are bit-identical
+// to the reference for finite inputs (dist AND lowest-index argmin) -- see DESIGN.md "Chamfer forward".
+//
+// Forward design (FP32-FMA-pipe bound, 8 algorithmic flop per directed pair):
+//   * one CTA = 32*Q queries of one cloud/direction; its 4 warps hold the SAME queries in registers and
+//     each scans a quarter of the targets, so an SM that hosts k CTAs puts k warps on each of its four
+//     sub-partitions (grid of 1024 CTAs on 148 SMs at B=32, N=M=2048 -> 6.92 CTAs/SM, all co-resident).
+//   * targets are staged per 1024-point tile in shared memory as SoA x[], y[], z[], w[] where the
+//     coordinates are centred on the cloud (t - c) and w = |t - c|^2; one broadcast LDS.128 per array
+//     feeds 4 targets to all lanes.
+//   * FILTER: a_k = w_k - 2 (q-c).(t_k-c) = |t_k-q|^2 - |q-c|^2 costs 3 FMAs per pair, issued as packed
+//     FFMA2 (two targets per instruction); the minimum over a 16-target chunk is taken with FMNMX3.
+//     Per chunk and query the kernel keeps (best chunk minimum, its chunk id, second-best chunk minimum).
+//   * EXACT: a rigorous rounding bound (margin = 2^-18 (|q-c| + max|t-c|)^2, derivation in DESIGN.md) says
+//     the reference's argmin lies in the best chunk whenever second > best + margin; that chunk (16
+//     targets) is re-evaluated with the reference's exact formula fma(dz,dz,fma(dx,dx,rn(dy*dy))) in index
+//     order with strict '<'.  Otherwise (near-ties, duplicated points, non-finite input) the query takes
+//     an exact full scan that also reproduces the reference's NaN/512-tile semantics.
+//   => dist/idx are always produced by the exact formula; the filter only decides where to look.
+#include "psd_common.cuh"
+
+namespace psd {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTile = 1024;     // targets per shared-memory tile (16 KB as 4 SoA arrays)
+constexpr int kChunk = 16;      // targets per filter chunk
+constexpr float kBig = 1e30f;   // padding value for w[]; larger than any admissible filter value
+constexpr float kLimit = 1e18f; // |t-c|^2, |q-c|^2 above this (or NaN) route the query to the exact scan
+constexpr int kRefTile = 512;   // the reference's tile (chamfer3D.cu:13), only observable with NaN inputs
+
+struct NNDirection {
+    const float *q;      // query cloud base
+    const float *t;      // target cloud base
+    long long q_ps, q_cs, q_bs;  // query strides in floats: point, component, batch
+    long long t_ps, t_cs, t_bs;
+    float *dist;         // [B, nq]
+    int *idx;            // [B, nq]
+    int nq, nt;
+    int q_begin, q_count;  // query slice handled by this launch
+    int qblocks;           // CTAs per cloud for this direction
+    int slot;              // 0/1: column in sums[B,2] / fs_count[B,2]
+};
+
+struct NNParams {
+    NNDirection dir[2];
+    int blocks_dir0;  // CTAs belonging to dir[0]
+    float *sums;      // optional [B,2]
+    int *fs_count;    // optional [B,2]
+    float fs_thr;
+};
+
+__device__ unsigned long long g_fallback_queries = 0ull;
+
+template <int Q>
+__global__ void __launch_bounds__(kThreads, (Q <= 4) ? 7 : 3) chamfer_nn_kernel(const NNParams p) {
+    constexpr int QB = 32 * Q;
+    constexpr int C = kChunk;
+    __shared__ __align__(16) float sX[kTile];
+    __shared__ __align__(16) float sY[kTile];
+    __shared__ __align__(16) float sZ[kTile];
+    __shared__ __align__(16) float sW[kTile];
+    __shared__ float s_wmax[kWarps];
+    __shared__ int s_bad[kWarps];
+    __shared__ int s_nfb;
+    __shared__ unsigned long long s_key[kWarps];
+    __shared__ float s_sum[kWarps];
+    __shared__ int s_cnt[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool second_dir = (int)blockIdx.x >= p.blocks_dir0;
+    const NNDirection &D = p.dir[second_dir ? 1 : 0];
+    const int bid = second_dir ? blockIdx.x - p.blocks_dir0 : blockIdx.x;
+    const int cloud = bid / D.qblocks;
+    const int qblock = bid - cloud * D.qblocks;
+    const int nt = D.nt;
+    const float *__restrict__ tb = D.t + (long long)cloud * D.t_bs;
+    const float *__restrict__ qb = D.q + (long long)cloud * D.q_bs;
+    const long long tps = D.t_ps, tcs = D.t_cs, qps = D.q_ps, qcs = D.q_cs;
+    const int q_end = D.q_begin + D.q_count;  // exclusive
+    const int q0 = D.q_begin + qblock * QB;
+
+    // centre of the filter's coordinate frame: mean of up to 8 evenly spaced targets.  Any value is
+    // correct (results come from the exact formula); a centred frame only keeps the margin small.
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    {
+        const int ns = nt < 8 ? nt : 8;
+        for (int s = 0; s < ns; ++s) {
+            const long long k = ((long long)s * nt) / ns;
+            cx += __ldg(tb + k * tps);
+            cy += __ldg(tb + k * tps + tcs);
+            cz += __ldg(tb + k * tps + 2 * tcs);
+        }
+        const float inv = 1.0f / (float)ns;
+        cx *= inv; cy *= inv; cz *= inv;
+    }
+
+    float qx[Q], qy[Q], qz[Q];  // -2 (q - c)
+    float best[Q], second[Q];
+    int bchunk[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        int j = q0 + i * 32 + lane;
+        j = j < q_end ? j : q_end - 1;
+        qx[i] = -2.0f * (__ldg(qb + j * qps) - cx);
+        qy[i] = -2.0f * (__ldg(qb + j * qps + qcs) - cy);
+        qz[i] = -2.0f * (__ldg(qb + j * qps + 2 * qcs) - cz);
+        best[i] = kBig; second[i] = kBig; bchunk[i] = 0;
+    }
+
+    float wmax = 0.f;
+    int bad = 0;
+
+    for (int t0 = 0; t0 < nt; t0 += kTile) {
+        const int cnt = min(kTile, nt - t0);
+        const int nchunks = (cnt + C - 1) / C;
+        __syncthreads();  // previous tile fully consumed
+        for (int k = tid; k < nchunks * C; k += kThreads) {
+            float x = 0.f, y = 0.f, z = 0.f, w = kBig;
+            if (k < cnt) {
+                const float *tp = tb + (long long)(t0 + k) * tps;
+                x = __ldg(tp) - cx;
+                y = __ldg(tp + tcs) - cy;
+                z = __ldg(tp + 2 * tcs) - cz;
+                w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
+                bad |= !(w < kLimit);
+                wmax = fmaxf(wmax, w);
+            }
+            sX[k] = x; sY[k] = y; sZ[k] = z; sW[k] = w;
+        }
+        __syncthreads();
+
+        const float4 *X4 = reinterpret_cast<const float4 *>(sX);
+        const float4 *Y4 = reinterpret_cast<const float4 *>(sY);
+        const float4 *Z4 = reinterpret_cast<const float4 *>(sZ);
+        const float4 *W4 = reinterpret_cast<const float4 *>(sW);
+        for (int c = warp; c < nchunks; c += kWarps) {
+            float cm[Q];
+#pragma unroll
+            for (int g = 0; g < C / 4; ++g) {
+                const float4 X = X4[c * (C / 4) + g];
+                const float4 Y = Y4[c * (C / 4) + g];
+                const float4 Z = Z4[c * (C / 4) + g];
+                const float4 W = W4[c * (C / 4) + g];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    float2 a01 = ffma2(qz[i], make_float2(Z.x, Z.y), make_float2(W.x, W.y));
+                    float2 a23 = ffma2(qz[i], make_float2(Z.z, Z.w), make_float2(W.z, W.w));
+                    a01 = ffma2(qy[i], make_float2(Y.x, Y.y), a01);
+                    a23 = ffma2(qy[i], make_float2(Y.z, Y.w), a23);
+                    a01 = ffma2(qx[i], make_float2(X.x, X.y), a01);
+                    a23 = ffma2(qx[i], make_float2(X.z, X.w), a23);
+                    if (g == 0) {
+                        cm[i] = fminf(fmin3(a01.x, a01.y, a23.x), a23.y);
+                    } else {
+                        cm[i] = fmin3(cm[i], a01.x, a01.y);
+                        cm[i] = fmin3(cm[i], a23.x, a23.y);
+                    }
+                }
+            }
+            const int gchunk = t0 / C + c;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                const float v = cm[i];
+                second[i] = fminf(second[i], fmaxf(best[i], v));
+                const bool lt = v < best[i];
+                best[i] = fminf(best[i], v);
+                bchunk[i] = lt ? gchunk : bchunk[i];
+            }
+        }
+    }
+
+    // ---- exchange the per-warp partial results through shared memory (tile buffers are free now)
+    __syncthreads();
+    float *pbest = sX;                            // [kWarps][QB]
+    float *psecond = sY;                          // [kWarps][QB]
+    int *pchunk = reinterpret_cast<int *>(sZ);    // [kWarps][QB]
+    int *fb_list = reinterpret_cast<int *>(sW);   // [QB]
+    static_assert(kWarps * QB <= kTile, "partial exchange must fit in one tile array");
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        pbest[warp * QB + i * 32 + lane] = best[i];
+        psecond[warp * QB + i * 32 + lane] = second[i];
+        pchunk[warp * QB + i * 32 + lane] = bchunk[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) { s_wmax[warp] = wmax; s_bad[warp] = bad; }
+    if (tid == 0) s_nfb = 0;
+    __syncthreads();
+    const float t2max = fmaxf(fmaxf(s_wmax[0], s_wmax[1]), fmaxf(s_wmax[2], s_wmax[3]));
+    const bool cta_bad = (s_bad[0] | s_bad[1] | s_bad[2] | s_bad[3]) != 0;
+    const float tmax = sqrtf(t2max);
+
+    float loc_sum = 0.f;
+    int loc_cnt = 0;
+    float *dist_out = D.dist + (long long)cloud * D.nq;
+    int *idx_out = D.idx + (long long)cloud * D.nq;
+
+    for (int ql = tid; ql < QB; ql += kThreads) {
+        const int j = q0 + ql;
+        if (j >= q_end) continue;
+        float b1 = kBig, b2 = kBig;
+        int bc = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const float v = pbest[w * QB + ql];
+            b2 = fminf(b2, fminf(psecond[w * QB + ql], fmaxf(b1, v)));
+            if (v < b1) { b1 = v; bc = pchunk[w * QB + ql]; }
+        }
+        const float x1 = __ldg(qb + j * qps), y1 = __ldg(qb + j * qps + qcs), z1 = __ldg(qb + j * qps + 2 * qcs);
+        const float ux = x1 - cx, uy = y1 - cy, uz = z1 - cz;
+        const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
+        const float r = sqrtf(qq) + tmax;
+        const float S = r * r;
+        const float margin = __fmaf_rn(S, 3.814697265625e-6f /* 2^-18 */, 1e-36f);
+        const bool ok = !cta_bad && (S < 4.0f * kLimit) && (b2 > b1 + margin);
+        if (ok) {
+            const int k0 = bc * C;
+            const int k1 = min(k0 + C, nt);
+            const float *tp = tb + (long long)k0 * tps;
+            float dbest = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
+            int ibest = k0;
+            for (int k = k0 + 1; k < k1; ++k) {
+                tp += tps;
+                const float d = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
+                if (d < dbest) { dbest = d; ibest = k; }
+            }
+            dist_out[j] = dbest;
+            idx_out[j] = ibest;
+            loc_sum += dbest;
+            loc_cnt += dbest < p.fs_thr;
+        } else {
+            fb_list[atomicAdd(&s_nfb, 1)] = ql;
+        }
+    }
+    __syncthreads();
+
+    // ---- exact full scan for the flagged queries (whole CTA per query).  Reference semantics incl. NaN:
+    // within a 512-target tile the first element is taken unconditionally and NaN never replaces or is
+    // replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+    const int nfb = s_nfb;
+    for (int f = 0; f < nfb; ++f) {
+        const int ql = fb_list[f];
+        const int j = q0 + ql;
+        const float x1 = __ldg(qb + j * qps), y1 = __ldg(qb + j * qps + qcs), z1 = __ldg(qb + j * qps + 2 * qcs);
+        unsigned long long key = ~0ull;
+        for (int k = tid; k < nt; k += kThreads) {
+            const float *tp = tb + (long long)k * tps;
+            const float d = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
+            const float *ts = tb + (long long)(k & ~(kRefTile - 1)) * tps;
+            const float dts = sqdist_exact(__ldg(ts) - x1, __ldg(ts + tcs) - y1, __ldg(ts + 2 * tcs) - z1);
+            if (!(d != d) && !(dts != dts)) {
+                const unsigned long long kk = pack_key(d, k);
+                key = kk < key ? kk : key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = shfl_xor_u64(key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0) s_key[warp] = key;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long kmin = s_key[0];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) kmin = s_key[w] < kmin ? s_key[w] : kmin;
+            const float d0 = sqdist_exact(__ldg(tb) - x1, __ldg(tb + tcs) - y1, __ldg(tb + 2 * tcs) - z1);
+            float dres;
+            int ires;
+            if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
+            else { dres = __uint_as_float((unsigned int)(kmin >> 32)); ires = (int)(kmin & 0xffffffffu); }
+            dist_out[j] = dres;
+            idx_out[j] = ires;
+            loc_sum += dres;
+            loc_cnt += dres < p.fs_thr;
+        }
+        __syncthreads();
+    }
+    if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries, (unsigned long long)nfb);
+
+    // ---- fused epilogues: per-cloud loss sums (loss/loss.py:36) and F-score counts (loss/loss_.py:132-133)
+    if (p.sums != nullptr || p.fs_count != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            loc_sum += __shfl_xor_sync(0xffffffffu, loc_sum, o);
+            loc_cnt += __shfl_xor_sync(0xffffffffu, loc_cnt, o);
+        }
+        if (lane == 0) { s_sum[warp] = loc_sum; s_cnt[warp] = loc_cnt; }
+        __syncthreads();
+        if (tid == 0) {
+            if (p.sums) atomicAdd(p.sums + cloud * 2 + D.slot, (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]));
+            if (p.fs_count) atomicAdd(p.fs_count + cloud * 2 + D.slot, s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward: replaces both NmDistanceGradKernel launches (chamfer3D.cu:155-195) with one kernel.
+// One thread per (direction, cloud, point).  g = 2*graddist; v = g*(a - b[idx]) with the subtraction
+// rounded before the multiply, exactly as the reference's SASS (FADD, FMUL, no FMA);
+// own-point term: grad_a[j] += v (unique address per direction -> plain red.add),
+// scatter term  : grad_b[idx] -= v, aggregated inside the warp first: lanes that hit the same target
+// (__match_any_sync on idx) are summed by the lowest lane of the group and issue one atomic per axis.
+// ------------------------------------------------------------------------------------------------
+struct GradParams {
+    const float *xyz1, *xyz2;
+    float *g1, *g2;
+    const float *gd1, *gd2;
+    const int *idx1, *idx2;
+    int b, n, m;
+    long long total1;  // b*n
+    long long total;   // b*(n+m)
+};
+
+__global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gid < p.total;
+    const bool d2 = gid >= p.total1;
+    const long long e = active ? (d2 ? gid - p.total1 : gid) : 0;  // flat (cloud, point) index in its direction
+    const int na = d2 ? p.m : p.n, nb = d2 ? p.n : p.m;
+    const float *a = d2 ? p.xyz2 : p.xyz1;
+    const float *bq = d2 ? p.xyz1 : p.xyz2;
+    float *ga = d2 ? p.g2 : p.g1;
+    float *gb = d2 ? p.g1 : p.g2;
+    const float *gd = d2 ? p.gd2 : p.gd1;
+    const int *idx = d2 ? p.idx2 : p.idx1;
+
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    long long tgt = -1 - (long long)(threadIdx.x & 31);  // inactive lanes: unique negative ids, never matched
+    if (active) {
+        const long long cloud = e / na;
+        const int j2 = idx[e];
+        const float g = gd[e] * 2.0f;
+        const float *pa = a + e * 3;
+        tgt = cloud * nb + j2;
+        const float *pb = bq + tgt * 3;
+        vx = __fmul_rn(g, __fsub_rn(pa[0], pb[0]));
+        vy = __fmul_rn(g, __fsub_rn(pa[1], pb[1]));
+        vz = __fmul_rn(g, __fsub_rn(pa[2], pb[2]));
+        float *o = ga + e * 3;
+        atomicAdd(o + 0, vx);
+        atomicAdd(o + 1, vy);
+        atomicAdd(o + 2, vz);
+    }
+    // warp-aggregated scatter (the direction is warp-uniform only if total1 % 32 == 0, so the direction
+    // bit is folded into the match key).
+    const unsigned long long mkey = ((unsigned long long)tgt << 1) | (unsigned long long)(d2 ? 1 : 0);
+    const unsigned int peers = __match_any_sync(0xffffffffu, mkey);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    float sx = vx, sy = vy, sz = vz;
+    // the lowest lane of every group adds its peers' terms in lane order; the loop trip count is the
+    // largest group size minus one (zero for clouds without shared nearest neighbours in the warp).
+    unsigned int rest = (lane == leader) ? (peers & ~(1u << lane)) : 0u;
+    while (__any_sync(0xffffffffu, rest != 0u)) {
+        const int src = rest ? __ffs(rest) - 1 : lane;
+        const float ox = __shfl_sync(0xffffffffu, vx, src);
+        const float oy = __shfl_sync(0xffffffffu, vy, src);
+        const float oz = __shfl_sync(0xffffffffu, vz, src);
+        if (rest) { sx += ox; sy += oy; sz += oz; rest &= rest - 1u; }
+    }
+    if (active && lane == leader) {
+        float *o = gb + tgt * 3;
+        atomicAdd(o + 0, -sx);
+        atomicAdd(o + 1, -sy);
+        atomicAdd(o + 2, -sz);
+    }
+}
+
+}  // namespace psd
+
+// ------------------------------------------------------------------------------------------------
+// host launchers (called by psd_capi.cu)
+// ------------------------------------------------------------------------------------------------
+using namespace psd;
+
+static inline int pick_q(long long total_queries, int num_sms) {
+    // 4 queries per thread (128 per CTA) unless the problem is so large that the CTA count is
+    // irrelevant for balance; Q=8 halves the shared-memory reads per pair.
+    (void)total_queries; (void)num_sms;
+    return 4;
+}
+
+cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
+                                       float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
+                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream) {
+    if (b <= 0 || n <= 0 || m <= 0) return cudaSuccess;
+    NNParams p;
+    const int Q = pick_q((long long)b * (n + m), 148);
+    const int QB = 32 * Q;
+    auto fill = [&](NNDirection &D, const float *q, int nq, const float *t, int nt, float *dist, int *idx, int slot) {
+        D.q = q; D.t = t; D.nq = nq; D.nt = nt; D.dist = dist; D.idx = idx; D.slot = slot;
+        if (layout == 0) { D.q_ps = 3; D.q_cs = 1; D.t_ps = 3; D.t_cs = 1; }
+        else { D.q_ps = 1; D.q_cs = nq; D.t_ps = 1; D.t_cs = nt; }
+        D.q_bs = 3LL * nq; D.t_bs = 3LL * nt;
+        int qb0 = q_begin < 0 ? 0 : q_begin;
+        if (qb0 > nq) qb0 = nq;
+        int qc = (q_count < 0) ? nq - qb0 : q_count;
+        if (qb0 + qc > nq) qc = nq - qb0;
+        D.q_begin = qb0; D.q_count = qc;
+        D.qblocks = (qc + QB - 1) / QB;
+    };
+    fill(p.dir[0], xyz1, n, xyz2, m, dist1, idx1, 0);
+    fill(p.dir[1], xyz2, m, xyz1, n, dist2, idx2, 1);
+    p.blocks_dir0 = b * p.dir[0].qblocks;
+    p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
+    const long long blocks = (long long)b * (p.dir[0].qblocks + p.dir[1].qblocks);
+    if (blocks == 0) return cudaSuccess;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    chamfer_nn_kernel<4><<<(unsigned int)blocks, kThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                        const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
+                                        int b, int n, int m, cudaStream_t stream) {
+    if (b <= 0 || (n <= 0 && m <= 0)) return cudaSuccess;
+    GradParams p;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.g1 = gradxyz1; p.g2 = gradxyz2; p.gd1 = graddist1; p.gd2 = graddist2;
+    p.idx1 = idx1; p.idx2 = idx2; p.b = b; p.n = n; p.m = m;
+    p.total1 = (long long)b * n;
+    p.total = (long long)b * (n + m);
+    const long long blocks = (p.total + 255) / 256;
+    chamfer_grad_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(fallback, g_fallback_queries, sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    if (reset) {
+        const unsigned long long z = 0;
+        e = cudaMemcpyToSymbol(g_fallback_queries, &z, sizeof(z));
+    }
+    return e;
+}

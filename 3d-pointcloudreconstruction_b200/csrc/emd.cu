@@ -1,0 +1,337 @@
+// emd.cu -- B200-native auction EMD (forward) and its gradient.
+//
+// Replaces metric/emd/emd_cuda.cu of the reference: the host loop of 7 launches per iteration
+// (clear, calc_unass_cnt, calc_unass_cnt_sum, calc_unass_idx, Bid, GetMax, Assign :23-215,256-268),
+// CalcDist (:217-226) and NmDistanceGradKernel (:284-300) become ONE persistent launch (+1 for the
+// gradient).  Clouds are independent, so the synchronisation scope is one cloud, not the grid: a cloud is
+// owned by a thread-block CLUSTER of S CTAs (S = 1,2,4,8 chosen so that B*S fills the 148 SMs) whose
+// per-cloud auction state lives in (distributed) shared memory for the whole run:
+//   replicated in every CTA : object coordinates xyz2 (SoA) and prices          (read in the O(u*n) scan)
+//   sliced by object owner  : max_increments, winner (the reference's max_idx), assignment_inv
+//   sliced by bidder home   : assignment, bid, bid_increments, the compacted bidder list
+// Per iteration: compact own unassigned points -> scan ALL objects for the own bidders (best / second-best
+// value, exact reference arithmetic) -> float atomicMax into the object owner's max_increments over DSMEM
+// -> cluster.sync -> winner = atomicMin(bidder index) among bidders within +-1e-6 of the maximum
+// -> cluster.sync -> winners commit: evict previous owner, broadcast the new price to every replica
+// -> cluster.sync.  The run stops early once no cloud point is unassigned (remaining iterations are no-ops).
+//
+// Arithmetic follows the reference bit for bit:
+//   s = fma(dz,dz, fma(dx,dx, rn(dy*dy))), d* = xyz2 - xyz1;  v = (float)(3.0 - (double)sqrtf(s) - (double)price)
+//   best: strict '>' in index order (lowest index wins ties), better: second best with multiplicity,
+//   both from -1e9;  increment = (best - better) + eps  (two fp32 roundings).
+// The only filter is a distance cut-off that is provably result-neutral: an object can change
+// (best, better) only if v > better, which requires sqrt(s) < 3 - better + 2e-6 (prices are >= 0).
+#include <cooperative_groups.h>
+#include <limits.h>
+
+#include "psd_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace psd {
+
+constexpr int kEmdThreads = 1024;
+constexpr float kNegInit = -1e9f;
+
+struct EmdParams {
+    const float *xyz1, *xyz2;
+    float *dist;
+    int *assignment;
+    float *price;          // may be NULL
+    int *assignment_inv;   // may be NULL
+    float *max_increments; // may be NULL
+    int *bid;              // may be NULL (written if given)
+    float *bid_increments; // may be NULL (written if given)
+    int b, n;
+    float eps;
+    int iters;
+    int fresh;  // 1: ignore the caller's state tensors and start from assignment = -1, price = 0
+};
+
+// float atomicMax with the reference's semantics (emd_cuda.cu:10-20): CAS loop, `val > old` in float.
+__device__ __forceinline__ void atomic_max_float(float *address, float val) {
+    int ret = __float_as_int(*reinterpret_cast<volatile float *>(address));
+    while (val > __int_as_float(ret)) {
+        const int old = ret;
+        if ((ret = atomicCAS(reinterpret_cast<int *>(address), old, __float_as_int(val))) == old) break;
+    }
+}
+
+struct Top2 {
+    float best, better;
+    int idx;
+};
+
+// merge two partial (best, second best with multiplicity, lowest index of best) results
+__device__ __forceinline__ void merge_top2(Top2 &a, float ob, float o2, int oi) {
+    if (ob > a.best) {
+        a.better = fmaxf(a.best, o2);
+        a.best = ob;
+        a.idx = oi;
+    } else if (ob == a.best) {
+        a.better = a.best;                      // two copies of the maximum -> second best equals it
+        a.idx = (oi >= 0 && (a.idx < 0 || oi < a.idx)) ? oi : a.idx;
+    } else {
+        a.better = fmaxf(a.better, ob);
+    }
+}
+
+__global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int cloud = blockIdx.x / S;
+    const int n = p.n;
+    const int ns = n / S;           // slice length (objects owned / bidders homed by this CTA)
+    const int base = rank * ns;     // first global index of the slice
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- shared memory carve-up (identical offsets in every CTA of the cluster)
+    float *ox = reinterpret_cast<float *>(smem_raw);
+    float *oy = ox + n;
+    float *oz = oy + n;
+    float *price = oz + n;
+    float *max_inc = price + n;                                // [ns] owner slice
+    int *winner = reinterpret_cast<int *>(max_inc + ns);        // [ns] owner slice
+    int *ass_inv = winner + ns;                                 // [ns] owner slice
+    int *assign = ass_inv + ns;                                 // [ns] home slice
+    int *bid = assign + ns;                                     // [ns] home slice
+    float *bid_inc = reinterpret_cast<float *>(bid + ns);       // [ns] home slice
+    int *list = reinterpret_cast<int *>(bid_inc + ns);          // [ns] compacted local bidder ids
+    float *w_best = reinterpret_cast<float *>(list + ns);       // [32] cross-warp merge scratch
+    float *w_better = w_best + 32;
+    int *w_idx = reinterpret_cast<int *>(w_better + 32);
+    int *ucount = w_idx + 32;                                   // [8] bidder count of every rank
+    int *cnt = ucount + 8;                                      // [1]
+
+    const float *x1g = p.xyz1 + (size_t)cloud * n * 3;
+    const float *x2g = p.xyz2 + (size_t)cloud * n * 3;
+    const size_t cb = (size_t)cloud * n;
+
+    // ---- load state (the caller pre-initialises it as emd_module.py:43-54; honour what is there)
+    for (int k = tid; k < n; k += kEmdThreads) {
+        ox[k] = x2g[k * 3 + 0];
+        oy[k] = x2g[k * 3 + 1];
+        oz[k] = x2g[k * 3 + 2];
+        price[k] = (p.price && !p.fresh) ? p.price[cb + k] : 0.f;
+    }
+    for (int k = tid; k < ns; k += kEmdThreads) {
+        max_inc[k] = (p.max_increments && !p.fresh) ? p.max_increments[cb + base + k] : 0.f;
+        winner[k] = INT_MAX;
+        ass_inv[k] = (p.assignment_inv && !p.fresh) ? p.assignment_inv[cb + base + k] : -1;
+        assign[k] = p.fresh ? -1 : p.assignment[cb + base + k];
+    }
+    cluster.sync();
+
+    for (int it = 0; it < p.iters; ++it) {
+        const bool last = (it == p.iters - 1);
+        // ---- 1. compact the unassigned points homed here (order is result-neutral, emd_cuda.cu:85-93)
+        if (tid == 0) *cnt = 0;
+        __syncthreads();
+        for (int k = tid; k < ns; k += kEmdThreads) {
+            const bool un = assign[k] == -1;
+            const unsigned int m = __ballot_sync(0xffffffffu, un);
+            int wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(cnt, __popc(m));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (un) list[wbase + __popc(m & ((1u << lane) - 1u))] = k;
+        }
+        __syncthreads();
+        const int u = *cnt;
+        if (tid < S) *cluster.map_shared_rank(ucount + rank, tid) = u;
+
+        // ---- 2./3. Bid (emd_cuda.cu:95-179): G bidders at a time, tpb threads per bidder
+        int G = 1;
+        while (G < u && G < kEmdThreads) G <<= 1;
+        const int tpb = kEmdThreads / G;
+        for (int a0 = 0; a0 < u; a0 += G) {
+            const int g = tid / tpb, t = tid - g * tpb;
+            const int a = a0 + g;
+            const bool valid = a < u;
+            const int jl = valid ? list[a] : 0;
+            const int j = base + jl;
+            const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
+            Top2 r;
+            r.best = kNegInit; r.better = kNegInit; r.idx = -1;
+            float R2 = 3.0e38f;
+            if (valid) {
+                for (int k = t; k < n; k += tpb) {
+                    const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+                    if (s <= R2) {
+                        const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
+                        if (v > r.best) {
+                            r.better = r.best; r.best = v; r.idx = k;
+                        } else if (v > r.better) {
+                            r.better = v;
+                        }
+                        const float R = (3.0f - r.better) + 2e-6f;
+                        R2 = R * R * 1.000001f;
+                    }
+                }
+            }
+            // merge inside the warp over min(tpb,32) lanes
+            const int wl = tpb < 32 ? tpb : 32;
+            for (int o = wl >> 1; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, r.best, o);
+                const float o2 = __shfl_xor_sync(0xffffffffu, r.better, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, r.idx, o);
+                merge_top2(r, ob, o2, oi);
+            }
+            if (tpb > 32) {  // bidder groups span several warps: finish through shared memory
+                __syncthreads();
+                if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }
+                __syncthreads();
+                if (t == 0) {
+                    const int wpb = tpb >> 5;
+                    for (int w = 1; w < wpb; ++w) merge_top2(r, w_best[warp + w], w_better[warp + w], w_idx[warp + w]);
+                }
+            }
+            if (valid && t == 0) {
+                const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
+                bid[jl] = r.idx;
+                bid_inc[jl] = inc;
+                if (r.idx >= 0) {
+                    const int orank = r.idx / ns;
+                    atomic_max_float(cluster.map_shared_rank(max_inc, orank) + (r.idx - orank * ns), inc);
+                }
+            }
+        }
+        cluster.sync();  // [A] all bids and max_increments visible cluster-wide
+
+        int total_u = 0;
+        for (int r2 = 0; r2 < S; ++r2) total_u += ucount[r2];
+        if (total_u == 0) break;  // uniform across the cluster; later iterations cannot change anything
+
+        // ---- 4. GetMax (emd_cuda.cu:181-194): lowest bidder index within +-1e-6 (fp64) of the maximum
+        for (int a = tid; a < u; a += kEmdThreads) {
+            const int jl = list[a];
+            const int o = bid[jl];
+            if (o >= 0) {
+                const int orank = o / ns, ol = o - orank * ns;
+                const double bi = (double)bid_inc[jl];
+                const double mi = (double)*(cluster.map_shared_rank(max_inc, orank) + ol);
+                if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMin(cluster.map_shared_rank(winner, orank) + ol, base + jl);
+            }
+        }
+        cluster.sync();  // [B]
+
+        // ---- 5. Assign (emd_cuda.cu:196-215)
+        for (int a = tid; a < u; a += kEmdThreads) {
+            const int jl = list[a];
+            const int o = bid[jl];
+            if (o >= 0) {
+                const int orank = o / ns, ol = o - orank * ns;
+                const int w = *(cluster.map_shared_rank(winner, orank) + ol);
+                if (last || w == base + jl) {
+                    const float inc = bid_inc[jl];
+                    int *inv = cluster.map_shared_rank(ass_inv, orank) + ol;
+                    const int old = *inv;
+                    if (!last && old != -1) {
+                        const int hr = old / ns;
+                        *(cluster.map_shared_rank(assign, hr) + (old - hr * ns)) = -1;
+                    }
+                    *inv = base + jl;
+                    assign[jl] = o;
+                    const float np = __fadd_rn(price[o], inc);
+                    for (int r2 = 0; r2 < S; ++r2) *(cluster.map_shared_rank(price, r2) + o) = np;
+                    *(cluster.map_shared_rank(max_inc, orank) + ol) = kNegInit;
+                    *(cluster.map_shared_rank(winner, orank) + ol) = INT_MAX;
+                }
+            }
+        }
+        cluster.sync();  // [C]
+    }
+
+    // ---- CalcDist (emd_cuda.cu:217-226) + write-back of the state the reference leaves in its tensors
+    for (int k = tid; k < ns; k += kEmdThreads) {
+        const int j = base + k;
+        const int o = assign[k];
+        float d = 0.f;
+        if (o >= 0)
+            d = sqdist_exact(x1g[j * 3 + 0] - ox[o], x1g[j * 3 + 1] - oy[o], x1g[j * 3 + 2] - oz[o]);
+        p.dist[cb + j] = d;
+        p.assignment[cb + j] = o;
+        if (p.assignment_inv) p.assignment_inv[cb + j] = ass_inv[k];
+        if (p.max_increments) p.max_increments[cb + j] = max_inc[k];
+        if (p.bid) p.bid[cb + j] = bid[k];
+        if (p.bid_increments) p.bid_increments[cb + j] = bid_inc[k];
+        if (p.price) p.price[cb + j] = price[j];
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until all remote accesses are done
+}
+
+// emd_cuda_backward's NmDistanceGradKernel (emd_cuda.cu:284-300): one term per address.
+__global__ void __launch_bounds__(256) emd_grad_kernel(int total, int n, const float *__restrict__ xyz1,
+                                                       const float *__restrict__ xyz2, const float *__restrict__ grad_dist,
+                                                       const int *__restrict__ idx, float *grad_xyz) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int cloud = e / n;
+    const int j2 = idx[e];
+    const float g = grad_dist[e] * 2.0f;
+    const float *a = xyz1 + (size_t)e * 3;
+    const float *bq = xyz2 + ((size_t)cloud * n + j2) * 3;
+    float *o = grad_xyz + (size_t)e * 3;
+    o[0] = __fadd_rn(o[0], __fmul_rn(g, __fsub_rn(a[0], bq[0])));
+    o[1] = __fadd_rn(o[1], __fmul_rn(g, __fsub_rn(a[1], bq[1])));
+    o[2] = __fadd_rn(o[2], __fmul_rn(g, __fsub_rn(a[2], bq[2])));
+}
+
+static size_t emd_smem_bytes(int n, int S) {
+    const int ns = n / S;
+    return sizeof(float) * (size_t)(4 * n) + sizeof(float) * (size_t)(7 * ns) + sizeof(float) * (32 * 3 + 8 + 4);
+}
+
+}  // namespace psd
+
+using namespace psd;
+
+// returns cudaSuccess, or an error; *unsupported is set when the shape does not fit the persistent kernel
+cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
+                                   float *price, int *assignment_inv, int *bid, float *bid_increments,
+                                   float *max_increments, float eps, int iters, int force_cluster, int fresh,
+                                   cudaStream_t stream, int *unsupported) {
+    *unsupported = 0;
+    if (b <= 0 || n <= 0) return cudaSuccess;
+    int dev = 0, num_sms = 148, max_smem = 227 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int S = 1;
+    if (force_cluster > 0) {
+        S = force_cluster;
+    } else {
+        while (S < 8 && b * (S * 2) <= num_sms) S *= 2;
+    }
+    while (S < 8 && emd_smem_bytes(n, S) > (size_t)max_smem) S *= 2;
+    if (emd_smem_bytes(n, S) > (size_t)max_smem || (n % S) != 0) { *unsupported = 1; return cudaSuccess; }
+    const size_t smem = emd_smem_bytes(n, S);
+    cudaError_t e = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    EmdParams p;
+    p.xyz1 = xyz1; p.xyz2 = xyz2; p.dist = dist; p.assignment = assignment; p.price = price;
+    p.assignment_inv = assignment_inv; p.max_increments = max_increments; p.bid = bid; p.bid_increments = bid_increments;
+    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned int)(b * S));
+    cfg.blockDim = dim3(kEmdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned int)S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, emd_auction_kernel, p);
+}
+
+cudaError_t psd_launch_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
+                                    const int *idx, int b, int n, cudaStream_t stream) {
+    if (b <= 0 || n <= 0) return cudaSuccess;
+    const int total = b * n;
+    emd_grad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(total, n, xyz1, xyz2, graddist, idx, gradxyz);
+    return cudaGetLastError();
+}

@@ -1,0 +1,213 @@
+// psd_capi.cu -- extern "C" surface of libpsd_b200.so (declared in include/psd_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/psd_b200.h"
+#include "psd_common.cuh"
+
+// launchers implemented in chamfer.cu / emd.cu
+cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
+                                       float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
+                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream);
+cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                        const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
+                                        int b, int n, int m, cudaStream_t stream);
+cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
+cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
+                                   float *price, int *assignment_inv, int *bid, float *bid_increments,
+                                   float *max_increments, float eps, int iters, int force_cluster, int fresh,
+                                   cudaStream_t stream, int *unsupported);
+cudaError_t psd_launch_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
+                                    const int *idx, int b, int n, cudaStream_t stream);
+
+static thread_local char g_err[512] = "";
+
+void psd_set_error(const char *what, cudaError_t err) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
+}
+void psd_set_error_msg(const char *what) { snprintf(g_err, sizeof(g_err), "%s", what); }
+
+static int finish(const char *what, cudaError_t e) {
+    if (e != cudaSuccess) {
+        psd_set_error(what, e);
+        (void)cudaGetLastError();  // clear the sticky launch error like the reference's cudaGetLastError() does
+        return 0;
+    }
+    return 1;
+}
+
+extern "C" {
+
+int psd_version(void) { return 1000; }
+
+const char *psd_last_error(void) { return g_err; }
+
+int psd_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                        int *idx1, int *idx2, void *stream) {
+    return finish("psd_chamfer_forward",
+                  psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, 0, dist1, dist2, idx1, idx2, nullptr, 0.f, nullptr, 0,
+                                             -1, (cudaStream_t)stream));
+}
+
+int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                           float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, int q_begin,
+                           int q_count, void *stream) {
+    if (layout != 0 && layout != 1) {
+        psd_set_error_msg("psd_chamfer_forward_ex: layout must be 0 ([B,N,3]) or 1 ([B,3,N])");
+        return -1;
+    }
+    return finish("psd_chamfer_forward_ex",
+                  psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums, fs_thr,
+                                             fs_count, q_begin, q_count, (cudaStream_t)stream));
+}
+
+int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
+                         int m, void *stream) {
+    return finish("psd_chamfer_backward",
+                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2, b, n, m,
+                                              (cudaStream_t)stream));
+}
+
+int psd_emd_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist, int *assignment,
+                    float *price, int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
+                    int *unass_idx, int *unass_cnt, int *unass_cnt_sum, int *cnt_tmp, int *max_idx, float eps,
+                    int iters, void *stream) {
+    (void)unass_idx; (void)unass_cnt; (void)unass_cnt_sum; (void)cnt_tmp; (void)max_idx;
+    // emd_cuda.cu:236-249 (the reference printf()s these and returns -1)
+    if (n != m) { psd_set_error_msg("Input Error! The two point clouds should have the same size."); return -1; }
+    if (b > 512) { psd_set_error_msg("Input Error! The batch size should be less than 512."); return -1; }
+    if (n % 1024 != 0) { psd_set_error_msg("Input Error! The size of the point clouds should be a multiple of 1024."); return -1; }
+    int unsupported = 0;
+    cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, price, assignment_inv, bid, bid_increments,
+                                           max_increments, eps, iters, 0, 0, (cudaStream_t)stream, &unsupported);
+    if (unsupported) {
+        psd_set_error_msg("psd_emd_forward: n too large for the shared-memory resident auction (n <= 8192 supported)");
+        return 0;
+    }
+    return finish("psd_emd_forward", e);
+}
+
+// test hook: force the cluster size (1,2,4,8) so that every decomposition can be parity-checked
+int psd_emd_forward_cluster(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
+                            float *price, int *assignment_inv, float eps, int iters, int cluster_size, void *stream) {
+    if (b > 512 || n % 1024 != 0) return -1;
+    int unsupported = 0;
+    cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, price, assignment_inv, nullptr, nullptr,
+                                           nullptr, eps, iters, cluster_size, 0, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg("psd_emd_forward_cluster: shape does not fit"); return 0; }
+    return finish("psd_emd_forward_cluster", e);
+}
+
+int psd_emd_forward_fresh(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment, float eps,
+                          int iters, void *stream) {
+    if (b > 512) { psd_set_error_msg("Input Error! The batch size should be less than 512."); return -1; }
+    if (n % 1024 != 0) { psd_set_error_msg("Input Error! The size of the point clouds should be a multiple of 1024."); return -1; }
+    int unsupported = 0;
+    cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                           eps, iters, 0, 1, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg("psd_emd_forward_fresh: n too large for the shared-memory resident auction (n <= 8192 supported)"); return 0; }
+    return finish("psd_emd_forward_fresh", e);
+}
+
+int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
+                     int b, int n, void *stream) {
+    return finish("psd_emd_backward", psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, (cudaStream_t)stream));
+}
+
+int psd_chamfer_stats(long long *out_host2, int reset) {
+    unsigned long long fb = 0;
+    cudaError_t e = psd_read_chamfer_stats(&fb, reset);
+    if (e != cudaSuccess) return finish("psd_chamfer_stats", e);
+    out_host2[0] = -1;  // filtered-path count is (total queries - fallbacks); not tracked on the device
+    out_host2[1] = (long long)fb;
+    return 1;
+}
+
+// ---- host-buffer entry point: stage through a grow-only device workspace owned by the library
+static float *g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+
+int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *dist1_host,
+                             float *dist2_host, int *idx1_host, int *idx2_host, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
+    const size_t need = sizeof(float) * (3 * s1 + 3 * s2 + 2 * s1 + 2 * s2);
+    if (need > g_ws_bytes) {
+        if (g_ws) cudaFree(g_ws);
+        g_ws = nullptr; g_ws_bytes = 0;
+        cudaError_t e = cudaMalloc(&g_ws, need);
+        if (e != cudaSuccess) return finish("psd_chamfer_forward_host(cudaMalloc)", e);
+        g_ws_bytes = need;
+    }
+    float *d_x1 = g_ws, *d_x2 = d_x1 + 3 * s1, *d_d1 = d_x2 + 3 * s2, *d_d2 = d_d1 + s1;
+    int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_x2, xyz2_host, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+        return finish("psd_chamfer_forward_host(H2D)", e);
+    e = psd_launch_chamfer_forward(d_x1, d_x2, b, n, m, 0, d_d1, d_d2, d_i1, d_i2, nullptr, 0.f, nullptr, 0, -1, stream);
+    if (e != cudaSuccess) return finish("psd_chamfer_forward_host(launch)", e);
+    if ((e = cudaMemcpyAsync(dist1_host, d_d1, sizeof(float) * s1, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(dist2_host, d_d2, sizeof(float) * s2, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(idx1_host, d_i1, sizeof(int) * s1, cudaMemcpyDeviceToHost, stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(idx2_host, d_i2, sizeof(int) * s2, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+        return finish("psd_chamfer_forward_host(D2H)", e);
+    return finish("psd_chamfer_forward_host(sync)", cudaStreamSynchronize(stream));
+}
+
+}  // extern "C"
+
+// ---- FP32 FMA peak microbenchmark (roofline denominator, measured live by bench.py)
+namespace {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float *out, int iters, float seed) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed * (float)(i + 1) + (float)threadIdx.x;
+    const float b = seed * 0.5f, c = seed * 0.25f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = __fmaf_rn(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int psd_fp32_fma_peak(float ms_target, float *tflops, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = num_sms * 8, block = 256;
+    float *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, sizeof(float) * grid * block);
+    if (e != cudaSuccess) return finish("psd_fp32_fma_peak(cudaMalloc)", e);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    // per launch: grid*block*iters*16 FMAs; at ~74 TFLOP/s, iters=4096 takes about 0.55 ms
+    int iters = 4096;
+    if (ms_target > 0.f) iters = (int)(4096.f * ms_target / 0.55f);
+    if (iters < 256) iters = 256;
+    ffma_peak_kernel<<<grid, block, 0, stream>>>(out, iters, 1.0001f);  // warm-up
+    float best_ms = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0, stream);
+        ffma_peak_kernel<<<grid, block, 0, stream>>>(out, iters, 1.0001f);
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best_ms) best_ms = ms;
+    }
+    e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (e != cudaSuccess) return finish("psd_fp32_fma_peak", e);
+    *tflops = (float)(2.0 * 16.0 * (double)iters * (double)grid * (double)block / ((double)best_ms * 1e-3) / 1e12);
+    return 1;
+}

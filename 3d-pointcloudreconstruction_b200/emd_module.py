@@ -1,0 +1,55 @@
+"""Drop-in for metric/emd/emd_module.py: ``emdModule()(xyz1, xyz2, eps, iters) -> dist, assignment``.
+
+Same contract as the reference (emd_module.py:9-19): clouds [B, n, 3] of equal size normalised to [0, 1],
+n a multiple of 1024, B <= 512; gradient only for xyz1 (xyz2 gets zeros); the assignment is approximate and
+not guaranteed to be a bijection.  The 12 scratch tensors of the reference wrapper (:43-54) are not needed:
+the persistent kernel keeps the auction state in shared memory and starts from the same initial state."""
+import torch
+from torch import nn
+from torch.autograd import Function
+
+try:
+    from . import _lib, emd
+except ImportError:
+    import _lib
+    import emd
+
+
+class emdFunction(Function):
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, eps, iters):
+        batchsize, n, _ = xyz1.size()
+        _, m, _ = xyz2.size()
+
+        assert n == m
+        assert xyz1.size()[0] == xyz2.size()[0]
+        assert n % 1024 == 0
+        assert batchsize <= 512
+
+        xyz1 = xyz1.contiguous().float().cuda()
+        xyz2 = xyz2.contiguous().float().cuda()
+        dist = torch.empty(batchsize, n, device=xyz1.device, dtype=torch.float32)
+        assignment = torch.empty(batchsize, n, device=xyz1.device, dtype=torch.int32)
+        rc = emd.forward_fresh(xyz1, xyz2, dist, assignment, eps, iters)
+        if rc != 1:
+            raise RuntimeError(f"emd.forward failed (rc={rc}): {_lib.last_error()}")
+        ctx.save_for_backward(xyz1, xyz2, assignment)
+        ctx.mark_non_differentiable(assignment)
+        return dist, assignment
+
+    @staticmethod
+    def backward(ctx, graddist, gradidx):
+        xyz1, xyz2, assignment = ctx.saved_tensors
+        graddist = graddist.contiguous()
+        gradxyz1 = torch.zeros(xyz1.size(), device=xyz1.device)
+        gradxyz2 = torch.zeros(xyz2.size(), device=xyz1.device)
+        _lib.raise_on_cuda_error(emd.backward(xyz1, xyz2, gradxyz1, graddist, assignment), "emd.backward")
+        return gradxyz1, gradxyz2, None, None
+
+
+class emdModule(nn.Module):
+    def __init__(self):
+        super(emdModule, self).__init__()
+
+    def forward(self, input1, input2, eps, iters):
+        return emdFunction.apply(input1, input2, eps, iters)

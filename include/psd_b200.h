@@ -1,0 +1,127 @@
+/*
+ * psd_b200.h -- C ABI of the B200-native point-set-distance library (libpsd_b200.so).
+ *
+ * Drop-in boundary for the hot path of sunhui-3D/3D-PointCloudReconstruction (3D-FENet): the two
+ * native modules `chamfer_3D` and `emd` that the reference binds with pybind11.  Every entry point
+ * below names the reference interface it replaces (paths relative to the reference repo root).
+ * Plain pointers and sizes only: no torch types cross this boundary.  All pointers are DEVICE
+ * pointers on the current CUDA device unless a name ends in `_host`; `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream, which is what the reference launches on).
+ *
+ * Layout contract (same as the reference, metric/chamfer3D/chamfer3D.cu:12-25, emd_cuda.cu:95-123):
+ * row-major contiguous fp32 clouds [B, N, 3], fp32 distances [B, N], int32 indices [B, N].
+ *
+ * Return convention (same as the reference): 1 = ok, 0 = CUDA error (message via psd_last_error(),
+ * the reference printf()s it), -1 = shape violation (EMD only, emd_cuda.cu:236-249).
+ * The kernels are asynchronous on `stream`; nothing here synchronises the host.
+ */
+#ifndef PSD_B200_H_
+#define PSD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library / ABI version: major * 1000 + minor. */
+int psd_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char *psd_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer distance.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces chamfer_3D.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+ *   = chamfer_forward, metric/chamfer3D/chamfer_cuda.cpp:17-19
+ *   -> chamfer_cuda_forward, metric/chamfer3D/chamfer3D.cu:136-154 (two NmDistanceKernel launches).
+ * dist1[b, j] = min_k |xyz1[b, j] - xyz2[b, k]|^2 evaluated as fma(dz,dz, fma(dx,dx, rn(dy*dy))) with
+ * d* = xyz2 - xyz1, idx1[b, j] = the lowest k attaining it; dist2/idx2 the same with the roles swapped.
+ * Bit-exact with the reference for finite inputs; NaN inputs follow the reference's 512-target-tile
+ * semantics (chamfer3D.cu:36,126).  One kernel launch for both directions. */
+int psd_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2,
+                        int *idx1, int *idx2, void *stream);
+
+/* Extended forward: the same NN search with fused epilogues and the generator's native layout.
+ *   layout   : 0 = [B, N, 3] (reference layout), 1 = [B, 3, N] (the model output before
+ *              fake.transpose(2,1), train.py:163 -- removes dist_chamfer_3D.py:79-80's .contiguous() copy).
+ *   sums     : optional [B, 2] fp32, sums[b] += (sum_j dist1[b, j], sum_k dist2[b, k])   (loss/loss.py:36)
+ *   fs_thr   : F-score threshold on the squared distances (loss/loss_.py:122, default 1e-4)
+ *   fs_count : optional [B, 2] int32, fs_count[b] += (#{dist1[b,:] < thr}, #{dist2[b,:] < thr})  (loss_.py:132-133)
+ * sums / fs_count are accumulated with atomics and must be zeroed by the caller.
+ * q_begin/q_count select a slice of the QUERY points of both directions (query sharding across GPUs:
+ * rank r passes its slice, targets stay whole); pass 0 and -1 for everything.  Outputs are still
+ * indexed by the global query index. */
+int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                           float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, int q_begin,
+                           int q_count, void *stream);
+
+/* Replaces chamfer_3D.backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+ *   = chamfer_backward, metric/chamfer3D/chamfer_cuda.cpp:22-26
+ *   -> chamfer_cuda_backward, metric/chamfer3D/chamfer3D.cu:176-195 (two NmDistanceGradKernel launches).
+ * ACCUMULATES into gradxyz1/gradxyz2 (the reference relies on caller-zeroed buffers, chamfer3D.cu:177-178):
+ *   g = 2*graddist1[b,j]; v = g*(xyz1[b,j]-xyz2[b,idx1[b,j]]); gradxyz1[b,j] += v; gradxyz2[b,idx1[b,j]] -= v
+ * and the mirror image for direction 2.  One launch; scatter uses warp-aggregated atomics. */
+int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
+                         int m, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Earth mover's distance, auction approximation.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces emd.forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments,
+ *                      max_increments, unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters)
+ *   = emd_forward, metric/emd/emd.cpp:12-17 -> emd_cuda_forward, metric/emd/emd_cuda.cu:228-282
+ *   (7 launches per iteration + CalcDist; here one persistent launch).
+ * Caller-initialised state exactly as metric/emd/emd_module.py:43-54: assignment = assignment_inv = -1,
+ * everything else 0.  dist and assignment are the results; price and assignment_inv are left in their final
+ * state; the remaining scratch tensors may be NULL (they are not needed by this implementation).
+ * Winner rule among bidders within +-1e-6 of an object's maximum increment: lowest bidder index
+ * (the reference's GetMax, emd_cuda.cu:188-191, is a last-writer-wins race).
+ * Returns -1 if m != n, b > 512 or n % 1024 != 0 (emd_cuda.cu:236-249). */
+int psd_emd_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist, int *assignment,
+                    float *price, int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
+                    int *unass_idx, int *unass_cnt, int *unass_cnt_sum, int *cnt_tmp, int *max_idx, float eps,
+                    int iters, void *stream);
+
+/* Same auction when the caller has no state to hand over: starts from assignment = -1, price = 0 inside the
+ * kernel (what emd_module.py:43-54 builds with 12 allocator calls and fills) and writes only dist and
+ * assignment.  One launch, no host-side fills. */
+int psd_emd_forward_fresh(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment, float eps,
+                          int iters, void *stream);
+
+/* Test hook (not part of the reference surface): the same auction with the cluster size forced to
+ * 1, 2, 4 or 8 CTAs per cloud, so that every decomposition can be parity-checked against the oracle. */
+int psd_emd_forward_cluster(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
+                            float *price, int *assignment_inv, float eps, int iters, int cluster_size, void *stream);
+
+/* Replaces emd.backward(xyz1, xyz2, gradxyz, graddist, idx)
+ *   = emd_backward, metric/emd/emd.cpp:19-23 -> emd_cuda_backward, metric/emd/emd_cuda.cu:302-316.
+ * gradxyz[b,j] += 2*graddist[b,j]*(xyz1[b,j] - xyz2[b,idx[b,j]]) (xyz1 only; emd_module.py:84-87). */
+int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
+                     int b, int n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
+ * stages them through its own device workspace on `stream` and copies the results back).
+ * ------------------------------------------------------------------------------------------- */
+int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *dist1_host,
+                             float *dist2_host, int *idx1_host, int *idx2_host, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers (used by bench.py; not part of the reference surface).
+ * ------------------------------------------------------------------------------------------- */
+
+/* FP32-FMA roofline denominator measured live: runs an FFMA-only kernel on every SM for roughly
+ * `ms_target` milliseconds and returns the achieved TFLOP/s (2 flop per FMA per lane) in *tflops. */
+int psd_fp32_fma_peak(float ms_target, float *tflops, void *stream);
+
+/* Counters of the chamfer forward's exact-fallback path since the last reset (diagnostics):
+ * out[0] = queries resolved by the filtered path, out[1] = queries that took the exact full scan. */
+int psd_chamfer_stats(long long *out_host2, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSD_B200_H_ */

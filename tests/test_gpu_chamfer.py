@@ -1,0 +1,169 @@
+"""GPU parity: CUDA chamfer path (through the C ABI) vs the CPU oracle, bit-exact dist AND idx."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_clouds
+
+pytestmark = pytest.mark.gpu
+
+
+def run_forward(pkg, dev, x, y):
+    tx, ty = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+    d1, d2, i1, i2 = pkg.chamfer_3DDist()(tx, ty)
+    torch.cuda.synchronize()
+    return d1.cpu().numpy(), d2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy()
+
+
+def assert_bit_equal(got, want, what):
+    for g, w, name in zip(got, want, ("dist1", "dist2", "idx1", "idx2")):
+        if g.dtype == np.float32:
+            same = (g.view(np.uint32) == w.view(np.uint32)) | (np.isnan(g) & np.isnan(w))
+        else:
+            same = g == w
+        assert same.all(), f"{what}: {name} differs at {np.argwhere(~same)[:5].tolist()} ({(~same).sum()} elements)"
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "lattice", "dup", "offset"])
+@pytest.mark.parametrize("shape", [(2, 1024, 1024), (3, 1000, 2000), (1, 1, 1), (2, 7, 513), (2, 515, 3), (1, 129, 1025), (4, 2048, 2048)])
+def test_forward_bit_exact(pkg, oracle, cuda, kind, shape):
+    b, n, m = shape
+    x, y = make_clouds(kind, b, n, m, seed=1234 + n + m)
+    got = run_forward(pkg, cuda, x, y)
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    assert_bit_equal(got, want, f"{kind} {shape}")
+
+
+def test_forward_full_size_config2(pkg, oracle, cuda):
+    """BASELINE.json configs[1]: B=32, N=M=2048, against the oracle on all 2.7e8 pairs."""
+    x, y = make_clouds("uniform", 32, 2048, 2048, seed=0)
+    got = run_forward(pkg, cuda, x, y)
+    want = oracle.chamfer_forward(x, y, nthreads=16)
+    assert_bit_equal(got, want, "config2")
+    fb = np.zeros(2, np.int64)
+    import ctypes
+    pkg._lib.lib.psd_chamfer_stats(fb.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), 0)
+    print("fallback queries so far:", fb[1])
+
+
+def test_forward_identical_clouds_and_all_duplicates(pkg, oracle, cuda):
+    x, _ = make_clouds("uniform", 2, 600, 600, seed=5)
+    got = run_forward(pkg, cuda, x, x.copy())
+    want = oracle.chamfer_forward(x, x.copy())
+    assert_bit_equal(got, want, "identical clouds")
+    assert (got[0] == 0).all() and (got[2] == np.arange(600)[None]).all()
+    y = np.repeat(x[:, :1], 700, axis=1).copy()  # every target is the same point: idx must be 0 everywhere
+    got = run_forward(pkg, cuda, x, y)
+    want = oracle.chamfer_forward(x, y)
+    assert_bit_equal(got, want, "all-duplicate targets")
+    assert (got[2] == 0).all()
+
+
+def test_forward_nan_inf_semantics(pkg, oracle, cuda):
+    """Non-finite inputs take the exact path, which follows the reference's 512-tile NaN behaviour."""
+    x, y = make_clouds("uniform", 2, 300, 1200, seed=9)
+    y[0, 0, 1] = np.nan      # poisons tile 0 of cloud 0 in direction 1
+    y[1, 700, 0] = np.nan    # a NaN inside tile 1 of cloud 1: ignored
+    y[1, 512, 2] = np.nan    # first element of tile 1 of cloud 1: the whole tile is lost
+    x[1, 5, 0] = np.inf
+    got = run_forward(pkg, cuda, x, y)
+    want = oracle.chamfer_forward(x, y)
+    assert_bit_equal(got, want, "nan/inf")
+
+
+def test_forward_huge_and_tiny_magnitudes(pkg, oracle, cuda):
+    x, y = make_clouds("uniform", 2, 256, 700, seed=11)
+    for scale in (1e-20, 1e-3, 1e4, 1e12, 3e19):
+        xs, ys = (x * np.float32(scale)).astype(np.float32), (y * np.float32(scale)).astype(np.float32)
+        got = run_forward(pkg, cuda, xs, ys)
+        want = oracle.chamfer_forward(xs, ys)
+        assert_bit_equal(got, want, f"scale {scale}")
+
+
+def test_backward_matches_oracle(pkg, oracle, cuda):
+    for kind, (b, n, m) in (("uniform", (4, 1024, 1024)), ("clustered", (3, 1000, 2000)), ("lattice", (2, 333, 77)), ("dup", (2, 512, 640))):
+        x, y = make_clouds(kind, b, n, m, seed=77)
+        tx = torch.from_numpy(x).to(cuda).requires_grad_(True)
+        ty = torch.from_numpy(y).to(cuda).requires_grad_(True)
+        d1, d2, i1, i2 = pkg.chamfer_3DDist()(tx, ty)
+        rng = np.random.default_rng(3)
+        g1 = rng.random((b, n), dtype=np.float32)
+        g2 = rng.random((b, m), dtype=np.float32)
+        (d1 * torch.from_numpy(g1).to(cuda)).sum().add((d2 * torch.from_numpy(g2).to(cuda)).sum()).backward()
+        want1, want2 = oracle.chamfer_backward(x, y, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
+        # fp32 atomics accumulate in arbitrary order: 1e-5 relative (BASELINE.json north_star), scaled per tensor
+        for got, want in ((tx.grad.cpu().numpy(), want1), (ty.grad.cpu().numpy(), want2)):
+            tol = 1e-5 * max(np.abs(want).max(), 1e-30)
+            assert np.abs(got - want).max() <= tol, (kind, np.abs(got - want).max(), tol)
+
+
+def test_backward_raw_accumulates_into_given_buffers(pkg, oracle, cuda):
+    """chamfer_3D.backward adds onto the caller's buffers (the reference relies on caller-zeroed grads)."""
+    x, y = make_clouds("uniform", 2, 256, 300, seed=21)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    d1, d2, i1, i2 = pkg.chamfer_3DDist()(tx, ty)
+    g1 = torch.ones_like(d1)
+    g2 = torch.ones_like(d2)
+    a1 = torch.full_like(tx, 0.5)
+    a2 = torch.full_like(ty, -0.25)
+    assert pkg.chamfer_3D.backward(tx, ty, a1, a2, g1, g2, i1, i2) == 1
+    w1, w2 = oracle.chamfer_backward(x, y, g1.cpu().numpy(), g2.cpu().numpy(), i1.cpu().numpy(), i2.cpu().numpy())
+    assert np.allclose(a1.cpu().numpy(), w1 + 0.5, rtol=1e-5, atol=1e-6)
+    assert np.allclose(a2.cpu().numpy(), w2 - 0.25, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_fscore_and_sums(pkg, oracle, cuda):
+    x, y = make_clouds("clustered", 4, 1500, 1100, seed=31)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    out = pkg.chamfer_fscore_fused(tx, ty, threshold=1e-4)
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    assert_bit_equal([out[k].cpu().numpy() for k in ("dist1", "dist2", "idx1", "idx2")], want, "fused")
+    c1, c2 = oracle.fscore_counts(want[0], want[1], 1e-4)
+    assert (out["counts"].cpu().numpy() == np.stack([c1, c2], 1)).all()
+    sums = out["sums"].cpu().numpy()
+    assert np.allclose(sums[:, 0], want[0].astype(np.float64).sum(1), rtol=1e-5)
+    assert np.allclose(sums[:, 1], want[1].astype(np.float64).sum(1), rtol=1e-5)
+    f, p1, p2 = pkg.fscore(out["dist1"], out["dist2"], 1e-4)
+    assert torch.equal(f, out["fscore"]) and torch.equal(p1, out["precision_1"]) and torch.equal(p2, out["precision_2"])
+
+
+def test_soa_layout_matches_aos(pkg, oracle, cuda):
+    """[B,3,N] input (the generator's native layout, train.py:163) gives the same bits without a transpose copy."""
+    x, y = make_clouds("uniform", 3, 777, 1029, seed=41)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    out = pkg.chamfer_fscore_fused(tx.transpose(1, 2).contiguous(), ty.transpose(1, 2).contiguous(), layout=1)
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    assert_bit_equal([out[k].cpu().numpy() for k in ("dist1", "dist2", "idx1", "idx2")], want, "soa")
+
+
+def test_query_slices_cover_whole(pkg, oracle, cuda):
+    """Query sharding: two launches over disjoint query slices reproduce the full result."""
+    x, y = make_clouds("uniform", 2, 1000, 1300, seed=51)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    d1 = torch.zeros(2, 1000, device=cuda); d2 = torch.zeros(2, 1300, device=cuda)
+    i1 = torch.zeros(2, 1000, device=cuda, dtype=torch.int32); i2 = torch.zeros(2, 1300, device=cuda, dtype=torch.int32)
+    # slices are expressed per direction through q_begin/q_count on the larger cloud; use halves of max(n, m)
+    for qb, qc in ((0, 650), (650, 650)):
+        assert pkg.chamfer_3D.forward_ex(tx, ty, d1, d2, i1, i2, q_begin=qb, q_count=qc) == 1
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    assert_bit_equal([t.cpu().numpy() for t in (d1, d2, i1, i2)], want, "slices")
+
+
+def test_host_buffer_entry_point(pkg, oracle, cuda):
+    import ctypes
+    x, y = make_clouds("uniform", 2, 512, 640, seed=61)
+    d1 = np.zeros((2, 512), np.float32); d2 = np.zeros((2, 640), np.float32)
+    i1 = np.zeros((2, 512), np.int32); i2 = np.zeros((2, 640), np.int32)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    rc = pkg._lib.lib.psd_chamfer_forward_host(vp(x), vp(y), 2, 512, 640, vp(d1), vp(d2), vp(i1), vp(i2), None)
+    assert rc == 1, pkg._lib.last_error()
+    assert_bit_equal((d1, d2, i1, i2), oracle.chamfer_forward(x, y), "host entry")
+
+
+def test_errors_are_loud(pkg, cuda):
+    x = torch.rand(2, 64, 3)
+    with pytest.raises(RuntimeError):
+        pkg.chamfer_3DDist()(x, x)  # CPU tensors: no fallback
+    xd = torch.rand(2, 64, 3, device=cuda, dtype=torch.float64)
+    with pytest.raises(RuntimeError):
+        pkg.chamfer_3DDist()(xd, xd)

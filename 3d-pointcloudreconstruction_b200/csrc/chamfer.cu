@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(kThreads, (Q <= 4) ? 7 : 3) chamfer_nn_kernel(
     float cx = 0.f, cy = 0.f, cz = 0.f;
     {
         const int ns = nt < 8 ? nt : 8;
+        const int step = nt >> 3;  // nt >= 8: samples at 0, nt/8, 2nt/8, ...; else every point
         for (int s = 0; s < ns; ++s) {
-            const long long k = ((long long)s * nt) / ns;
+            const long long k = nt < 8 ? s : s * step;
             cx += __ldg(tb + k * tps);
             cy += __ldg(tb + k * tps + tcs);
             cz += __ldg(tb + k * tps + 2 * tcs);
@@ -113,23 +114,67 @@ __global__ void __launch_bounds__(kThreads, (Q <= 4) ? 7 : 3) chamfer_nn_kernel(
 
     float wmax = 0.f;
     int bad = 0;
+    // 16-byte aligned AoS cloud: tiles (multiples of 1024 points = 12288 B) can be read as float4
+    const bool vec_ok = (tps == 3) && (tcs == 1) && ((reinterpret_cast<unsigned long long>(tb) & 15ull) == 0ull);
 
     for (int t0 = 0; t0 < nt; t0 += kTile) {
         const int cnt = min(kTile, nt - t0);
         const int nchunks = (cnt + C - 1) / C;
         __syncthreads();  // previous tile fully consumed
-        for (int k = tid; k < nchunks * C; k += kThreads) {
-            float x = 0.f, y = 0.f, z = 0.f, w = kBig;
-            if (k < cnt) {
-                const float *tp = tb + (long long)(t0 + k) * tps;
-                x = __ldg(tp) - cx;
-                y = __ldg(tp + tcs) - cy;
-                z = __ldg(tp + 2 * tcs) - cz;
-                w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
-                bad |= !(w < kLimit);
-                wmax = fmaxf(wmax, w);
+        if (vec_ok && cnt == kTile) {
+            // AoS fast path: 6 x LDG.128 = 24 floats = 8 whole points per thread, all loads in flight at once
+            const float4 *src = reinterpret_cast<const float4 *>(tb + (long long)t0 * 3) + tid * 6;
+            float f[24];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float4 v = __ldg(src + i);
+                f[4 * i + 0] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
             }
-            sX[k] = x; sY[k] = y; sZ[k] = z; sW[k] = w;
+            float xs[8], ys[8], zs[8], ws[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xs[i] = f[3 * i + 0] - cx;
+                ys[i] = f[3 * i + 1] - cy;
+                zs[i] = f[3 * i + 2] - cz;
+                ws[i] = __fmaf_rn(zs[i], zs[i], __fmaf_rn(xs[i], xs[i], ys[i] * ys[i]));
+                bad |= !(ws[i] < kLimit);
+                wmax = fmaxf(wmax, ws[i]);
+            }
+            float4 *dX = reinterpret_cast<float4 *>(sX) + tid * 2, *dY = reinterpret_cast<float4 *>(sY) + tid * 2;
+            float4 *dZ = reinterpret_cast<float4 *>(sZ) + tid * 2, *dW = reinterpret_cast<float4 *>(sW) + tid * 2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                dX[h] = make_float4(xs[4 * h], xs[4 * h + 1], xs[4 * h + 2], xs[4 * h + 3]);
+                dY[h] = make_float4(ys[4 * h], ys[4 * h + 1], ys[4 * h + 2], ys[4 * h + 3]);
+                dZ[h] = make_float4(zs[4 * h], zs[4 * h + 1], zs[4 * h + 2], zs[4 * h + 3]);
+                dW[h] = make_float4(ws[4 * h], ws[4 * h + 1], ws[4 * h + 2], ws[4 * h + 3]);
+            }
+        } else {
+            // generic strides / ragged tile: 4 points per thread per round, loads issued before use
+            for (int k0 = tid; k0 < nchunks * C; k0 += 4 * kThreads) {
+                float lx[4], ly[4], lz[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + i * kThreads;
+                    const bool in = k < cnt;
+                    const float *tp = tb + (long long)(t0 + (in ? k : 0)) * tps;
+                    lx[i] = __ldg(tp); ly[i] = __ldg(tp + tcs); lz[i] = __ldg(tp + 2 * tcs);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = k0 + i * kThreads;
+                    if (k < nchunks * C) {
+                        float x = 0.f, y = 0.f, z = 0.f, w = kBig;
+                        if (k < cnt) {
+                            x = lx[i] - cx; y = ly[i] - cy; z = lz[i] - cz;
+                            w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
+                            bad |= !(w < kLimit);
+                            wmax = fmaxf(wmax, w);
+                        }
+                        sX[k] = x; sY[k] = y; sZ[k] = z; sW[k] = w;
+                    }
+                }
+            }
         }
         __syncthreads();
 

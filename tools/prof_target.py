@@ -1,0 +1,24 @@
+"""Small fixed workload for ncu: 3x chamfer forward, 3x backward, 1x EMD at BASELINE configs 2/3."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import psd_b200
+pkg = psd_b200.load()
+dev = torch.device("cuda:0")
+B, N = 32, 2048
+torch.manual_seed(0)
+x = torch.rand(B, N, 3).to(dev); y = torch.rand(B, N, 3).to(dev)
+d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, N, device=dev)
+i1 = torch.empty(B, N, device=dev, dtype=torch.int32); i2 = torch.empty(B, N, device=dev, dtype=torch.int32)
+g1 = torch.rand(B, N, device=dev); g2 = torch.rand(B, N, device=dev)
+gx1 = torch.zeros(B, N, 3, device=dev); gx2 = torch.zeros(B, N, 3, device=dev)
+dist = torch.empty(B, N, device=dev); ass = torch.empty(B, N, device=dev, dtype=torch.int32)
+for _ in range(3):
+    assert pkg.chamfer_3D.forward(x, y, d1, d2, i1, i2) == 1
+for _ in range(3):
+    assert pkg.chamfer_3D.backward(x, y, gx1, gx2, g1, g2, i1, i2) == 1
+if "--no-emd" not in sys.argv:
+    assert pkg.emd.forward_fresh(x, y, dist, ass, 0.005, 50) == 1
+torch.cuda.synchronize()
+print("ok", float(d1.sum()), int(ass.sum()))

@@ -36,7 +36,7 @@ def load_ref():
 
 def main():
     B, N = 32, 2048
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and sys.argv[1].isdigit():
         B, N = int(sys.argv[1]), int(sys.argv[2])
     torch.manual_seed(0)
     x = torch.rand(B, N, 3).to(dev); y = torch.rand(B, N, 3).to(dev)
@@ -57,6 +57,14 @@ def main():
     tf = ctypes.c_float(0)
     pkg._lib.lib.psd_fp32_fma_peak(ctypes.c_float(1.0), ctypes.byref(tf), None)
     print(f"measured FP32 FMA peak: {tf.value:.2f} TFLOP/s")
+    def many(fn, k=20):
+        def f():
+            for _ in range(k):
+                fn()
+        return f
+    for name, fn, k in (("chamfer fwd x20", many(fwd), 20), ("chamfer bwd x20", many(lambda: pkg.chamfer_3D.backward(x, y, gx1, gx2, g1, g2, i1, i2)), 20)):
+        best, med = timeit(fn, reps=10, warm=2)
+        print(f"{name:24s} per launch: best {best / k:8.2f} us  median {med / k:8.2f} us   {8 * pairs / (med / k * 1e-6) / 1e12:.2f} TFLOP/s-equivalent")
     for name, fn in (("chamfer fwd", fwd), ("chamfer bwd(+zero)", bwd), ("chamfer fwd+bwd", both)):
         best, med = timeit(fn)
         print(f"{name:24s} best {best:8.1f} us  median {med:8.1f} us   {pairs / (med * 1e-6) / 1e12:.3f} Tpairs/s  "
@@ -74,6 +82,8 @@ def main():
     pkg._lib.lib.psd_chamfer_stats(fb.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), 0)
     print("fallback queries total:", fb[1])
 
+    if "--no-emd" in sys.argv:
+        return
     # EMD
     n = N
     dist = torch.empty(B, n, device=dev); ass = torch.empty(B, n, device=dev, dtype=torch.int32)

@@ -24,13 +24,15 @@
 
 namespace psd {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 16;        // one persistent CTA per SM: 4 warps on each of the four sub-partitions
 constexpr int kThreads = kWarps * 32;
-constexpr int kTile = 1024;     // targets per shared-memory tile (16 KB as 4 SoA arrays)
-constexpr int kChunk = 16;      // targets per filter chunk
-constexpr float kBig = 1e30f;   // padding value for w[]; larger than any admissible filter value
-constexpr float kLimit = 1e18f; // |t-c|^2, |q-c|^2 above this (or NaN) route the query to the exact scan
-constexpr int kRefTile = 512;   // the reference's tile (chamfer3D.cu:13), only observable with NaN inputs
+constexpr int kQ = 4;             // queries per lane
+constexpr int kQB = 32 * kQ;      // queries per block (every warp of the CTA holds the same 128 queries)
+constexpr int kChunk = 16;        // targets per filter chunk
+constexpr float kBig = 1e30f;     // padding value for w[]; larger than any admissible filter value
+constexpr float kLimit = 1e18f;   // |t-c|^2, |q-c|^2 above this (or NaN) route the query to the exact scan
+constexpr int kRefTile = 512;     // the reference's tile (chamfer3D.cu:13), only observable with NaN inputs
+constexpr int kPartBytes = kWarps * kQB * 12;  // per-block partial results: (best, second, chunk) per warp and query
 
 struct NNDirection {
     const float *q;      // query cloud base
@@ -41,309 +43,442 @@ struct NNDirection {
     int *idx;            // [B, nq]
     int nq, nt;
     int q_begin, q_count;  // query slice handled by this launch
-    int qblocks;           // CTAs per cloud for this direction
+    int qblocks;           // 128-query blocks per cloud for this direction
     int slot;              // 0/1: column in sums[B,2] / fs_count[B,2]
 };
 
 struct NNParams {
     NNDirection dir[2];
-    int blocks_dir0;  // CTAs belonging to dir[0]
-    float *sums;      // optional [B,2]
-    int *fs_count;    // optional [B,2]
+    int blocks_dir0;    // blocks belonging to dir[0]
+    int total_blocks;
+    int tile;           // targets per shared-memory tile (multiple of 1024)
+    int flush;          // blocks whose partial results fit in shared memory between two resolve phases
+    float *sums;        // optional [B,2]
+    int *fs_count;      // optional [B,2]
     float fs_thr;
 };
 
 __device__ unsigned long long g_fallback_queries = 0ull;
 
-template <int Q>
-__global__ void __launch_bounds__(kThreads, (Q <= 4) ? 7 : 3) chamfer_nn_kernel(const NNParams p) {
-    constexpr int QB = 32 * Q;
-    constexpr int C = kChunk;
-    __shared__ __align__(16) float sX[kTile];
-    __shared__ __align__(16) float sY[kTile];
-    __shared__ __align__(16) float sZ[kTile];
-    __shared__ __align__(16) float sW[kTile];
-    __shared__ float s_wmax[kWarps];
-    __shared__ int s_bad[kWarps];
+struct BlockInfo {      // per block of the current flush group (shared memory)
+    int blk, d, cloud, qblock;   // static part, filled once per flush group (the only integer divisions)
+    float cx, cy, cz;   // centre of the filter frame
+    float t2max;        // max |t-c|^2 over the target cloud
+    int bad;            // non-finite / huge target seen
+    int pad[3];
+};
+constexpr int kPerBlockBytes = kPartBytes + (int)sizeof(BlockInfo) + 3 * kQB * 4 + kQB * 4;  // + staged queries + fallback list
+
+// exact squared distance of query (x1,y1,z1) to target k of a cloud with generic strides
+__device__ __forceinline__ float exact_d(const float *__restrict__ tb, long long tps, long long tcs, int k, float x1,
+                                         float y1, float z1) {
+    const float *tp = tb + (long long)k * tps;
+    return sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
+}
+
+template <int TM>
+__global__ void __launch_bounds__(kThreads, 1) chamfer_nn_kernel(const NNParams p) {
+    constexpr int Q = kQ, QB = kQB, C = kChunk;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sX = reinterpret_cast<float *>(smem_raw);               // SoA target tile: x, y, z, w = |t-c|^2
+    float *sY = sX + TM;
+    float *sZ = sY + TM;
+    float *sW = sZ + TM;
+    float *part_best = sW + TM;                                   // [flush][kWarps][QB]
+    float *part_second = part_best + p.flush * kWarps * QB;
+    int *part_chunk = reinterpret_cast<int *>(part_second + p.flush * kWarps * QB);
+    float *sq = reinterpret_cast<float *>(part_chunk + p.flush * kWarps * QB);   // [flush][3][QB] staged raw queries
+    int *fb_list = reinterpret_cast<int *>(sq + p.flush * 3 * QB);               // [flush*QB]
+    BlockInfo *binfo = reinterpret_cast<BlockInfo *>(fb_list + p.flush * QB);    // [flush]
+    __shared__ float s_tile_wmax;
+    __shared__ int s_tile_bad;
     __shared__ int s_nfb;
     __shared__ unsigned long long s_key[kWarps];
-    __shared__ float s_sum[kWarps];
-    __shared__ int s_cnt[kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool second_dir = (int)blockIdx.x >= p.blocks_dir0;
-    const NNDirection &D = p.dir[second_dir ? 1 : 0];
-    const int bid = second_dir ? blockIdx.x - p.blocks_dir0 : blockIdx.x;
-    const int cloud = bid / D.qblocks;
-    const int qblock = bid - cloud * D.qblocks;
-    const int nt = D.nt;
-    const float *__restrict__ tb = D.t + (long long)cloud * D.t_bs;
-    const float *__restrict__ qb = D.q + (long long)cloud * D.q_bs;
-    const long long tps = D.t_ps, tcs = D.t_cs, qps = D.q_ps, qcs = D.q_cs;
-    const int q_end = D.q_begin + D.q_count;  // exclusive
-    const int q0 = D.q_begin + qblock * QB;
+    const int G = gridDim.x;
+    const int blk_begin = (int)(((long long)blockIdx.x * p.total_blocks) / G);
+    const int blk_end = (int)(((long long)(blockIdx.x + 1) * p.total_blocks) / G);
 
-    // centre of the filter's coordinate frame: mean of up to 8 evenly spaced targets.  Any value is
-    // correct (results come from the exact formula); a centred frame only keeps the margin small.
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    {
-        const int ns = nt < 8 ? nt : 8;
-        const int step = nt >> 3;  // nt >= 8: samples at 0, nt/8, 2nt/8, ...; else every point
-        for (int s = 0; s < ns; ++s) {
-            const long long k = nt < 8 ? s : s * step;
-            cx += __ldg(tb + k * tps);
-            cy += __ldg(tb + k * tps + tcs);
-            cz += __ldg(tb + k * tps + 2 * tcs);
-        }
-        const float inv = 1.0f / (float)ns;
-        cx *= inv; cy *= inv; cz *= inv;
-    }
+    float cx = 0.f, cy = 0.f, cz = 0.f;   // filter-frame centre of group c_group
+    int c_group = -1;
+    // shared-memory resident tile: (group = dir,cloud; first target) and its statistics
+    int res_group = -1, res_t0 = -1;
+    float res_wmax = 0.f;
+    int res_bad = 0;
 
-    float qx[Q], qy[Q], qz[Q];  // -2 (q - c)
-    float best[Q], second[Q];
-    int bchunk[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        int j = q0 + i * 32 + lane;
-        j = j < q_end ? j : q_end - 1;
-        qx[i] = -2.0f * (__ldg(qb + j * qps) - cx);
-        qy[i] = -2.0f * (__ldg(qb + j * qps + qcs) - cy);
-        qz[i] = -2.0f * (__ldg(qb + j * qps + 2 * qcs) - cz);
-        best[i] = kBig; second[i] = kBig; bchunk[i] = 0;
-    }
-
-    float wmax = 0.f;
-    int bad = 0;
-    // 16-byte aligned AoS cloud: tiles (multiples of 1024 points = 12288 B) can be read as float4
-    const bool vec_ok = (tps == 3) && (tcs == 1) && ((reinterpret_cast<unsigned long long>(tb) & 15ull) == 0ull);
-
-    for (int t0 = 0; t0 < nt; t0 += kTile) {
-        const int cnt = min(kTile, nt - t0);
-        const int nchunks = (cnt + C - 1) / C;
-        __syncthreads();  // previous tile fully consumed
-        if (vec_ok && cnt == kTile) {
-            // AoS fast path: 6 x LDG.128 = 24 floats = 8 whole points per thread, all loads in flight at once
-            const float4 *src = reinterpret_cast<const float4 *>(tb + (long long)t0 * 3) + tid * 6;
-            float f[24];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const float4 v = __ldg(src + i);
-                f[4 * i + 0] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
-            }
-            float xs[8], ys[8], zs[8], ws[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                xs[i] = f[3 * i + 0] - cx;
-                ys[i] = f[3 * i + 1] - cy;
-                zs[i] = f[3 * i + 2] - cz;
-                ws[i] = __fmaf_rn(zs[i], zs[i], __fmaf_rn(xs[i], xs[i], ys[i] * ys[i]));
-                bad |= !(ws[i] < kLimit);
-                wmax = fmaxf(wmax, ws[i]);
-            }
-            float4 *dX = reinterpret_cast<float4 *>(sX) + tid * 2, *dY = reinterpret_cast<float4 *>(sY) + tid * 2;
-            float4 *dZ = reinterpret_cast<float4 *>(sZ) + tid * 2, *dW = reinterpret_cast<float4 *>(sW) + tid * 2;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                dX[h] = make_float4(xs[4 * h], xs[4 * h + 1], xs[4 * h + 2], xs[4 * h + 3]);
-                dY[h] = make_float4(ys[4 * h], ys[4 * h + 1], ys[4 * h + 2], ys[4 * h + 3]);
-                dZ[h] = make_float4(zs[4 * h], zs[4 * h + 1], zs[4 * h + 2], zs[4 * h + 3]);
-                dW[h] = make_float4(ws[4 * h], ws[4 * h + 1], ws[4 * h + 2], ws[4 * h + 3]);
-            }
-        } else {
-            // generic strides / ragged tile: 4 points per thread per round, loads issued before use
-            for (int k0 = tid; k0 < nchunks * C; k0 += 4 * kThreads) {
-                float lx[4], ly[4], lz[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = k0 + i * kThreads;
-                    const bool in = k < cnt;
-                    const float *tp = tb + (long long)(t0 + (in ? k : 0)) * tps;
-                    lx[i] = __ldg(tp); ly[i] = __ldg(tp + tcs); lz[i] = __ldg(tp + 2 * tcs);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int k = k0 + i * kThreads;
-                    if (k < nchunks * C) {
-                        float x = 0.f, y = 0.f, z = 0.f, w = kBig;
-                        if (k < cnt) {
-                            x = lx[i] - cx; y = ly[i] - cy; z = lz[i] - cz;
-                            w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
-                            bad |= !(w < kLimit);
-                            wmax = fmaxf(wmax, w);
-                        }
-                        sX[k] = x; sY[k] = y; sZ[k] = z; sW[k] = w;
-                    }
-                }
-            }
+    for (int fb0 = blk_begin; fb0 < blk_end; fb0 += p.flush) {
+        const int nb = min(p.flush, blk_end - fb0);
+        // =========================== set-up: decode the blocks and stage their queries in shared memory
+        if (tid < nb) {
+            BlockInfo bi;
+            bi.blk = fb0 + tid;
+            bi.d = bi.blk >= p.blocks_dir0 ? 1 : 0;
+            const int bid = bi.d ? bi.blk - p.blocks_dir0 : bi.blk;
+            const int qbn = p.dir[bi.d].qblocks;
+            bi.cloud = bid / qbn;
+            bi.qblock = bid - bi.cloud * qbn;
+            bi.cx = bi.cy = bi.cz = 0.f; bi.t2max = 0.f; bi.bad = 0; bi.pad[0] = bi.pad[1] = bi.pad[2] = 0;
+            binfo[tid] = bi;
         }
         __syncthreads();
+        for (int i = tid; i < nb * QB; i += kThreads) {
+            const int bl = i / QB, ql = i - bl * QB;
+            const BlockInfo &bi = binfo[bl];
+            const NNDirection &D = p.dir[bi.d];
+            const float *__restrict__ qb = D.q + (long long)bi.cloud * D.q_bs;
+            int j = D.q_begin + bi.qblock * QB + ql;
+            const int q_last = D.q_begin + D.q_count - 1;
+            j = j < q_last ? j : q_last;
+            sq[(bl * 3 + 0) * QB + ql] = __ldg(qb + j * D.q_ps);
+            sq[(bl * 3 + 1) * QB + ql] = __ldg(qb + j * D.q_ps + D.q_cs);
+            sq[(bl * 3 + 2) * QB + ql] = __ldg(qb + j * D.q_ps + 2 * D.q_cs);
+        }
+        if (tid == 0) s_nfb = 0;
+        __syncthreads();
 
-        const float4 *X4 = reinterpret_cast<const float4 *>(sX);
-        const float4 *Y4 = reinterpret_cast<const float4 *>(sY);
-        const float4 *Z4 = reinterpret_cast<const float4 *>(sZ);
-        const float4 *W4 = reinterpret_cast<const float4 *>(sW);
-        for (int c = warp; c < nchunks; c += kWarps) {
-            float cm[Q];
+        // =========================== stage A: filter scan, one block after the other (no barrier between
+        // blocks while the target tile stays resident: warps run ahead independently)
+        for (int bl = 0; bl < nb; ++bl) {
+            const int d = binfo[bl].d, cloud = binfo[bl].cloud;
+            const NNDirection &D = p.dir[d];
+            const int nt = D.nt;
+            const float *__restrict__ tb = D.t + (long long)cloud * D.t_bs;
+            const long long tps = D.t_ps, tcs = D.t_cs;
+            const int group = d * 0x40000000 + cloud;
+
+            // centre of the filter's coordinate frame: mean of up to 8 evenly spaced targets.  Any value is
+            // correct (results come from the exact formula); a centred frame only keeps the margin small.
+            if (group != c_group) {
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                const int ns = nt < 8 ? nt : 8;
+                const int step = nt >> 3;
 #pragma unroll
-            for (int g = 0; g < C / 4; ++g) {
-                const float4 X = X4[c * (C / 4) + g];
-                const float4 Y = Y4[c * (C / 4) + g];
-                const float4 Z = Z4[c * (C / 4) + g];
-                const float4 W = W4[c * (C / 4) + g];
-#pragma unroll
-                for (int i = 0; i < Q; ++i) {
-                    float2 a01 = ffma2(qz[i], make_float2(Z.x, Z.y), make_float2(W.x, W.y));
-                    float2 a23 = ffma2(qz[i], make_float2(Z.z, Z.w), make_float2(W.z, W.w));
-                    a01 = ffma2(qy[i], make_float2(Y.x, Y.y), a01);
-                    a23 = ffma2(qy[i], make_float2(Y.z, Y.w), a23);
-                    a01 = ffma2(qx[i], make_float2(X.x, X.y), a01);
-                    a23 = ffma2(qx[i], make_float2(X.z, X.w), a23);
-                    if (g == 0) {
-                        cm[i] = fminf(fmin3(a01.x, a01.y, a23.x), a23.y);
-                    } else {
-                        cm[i] = fmin3(cm[i], a01.x, a01.y);
-                        cm[i] = fmin3(cm[i], a23.x, a23.y);
+                for (int s = 0; s < 8; ++s) {
+                    if (s < ns) {
+                        const long long k = nt < 8 ? s : s * step;
+                        sx += __ldg(tb + k * tps);
+                        sy += __ldg(tb + k * tps + tcs);
+                        sz += __ldg(tb + k * tps + 2 * tcs);
                     }
                 }
+                const float inv = 1.0f / (float)ns;
+                cx = sx * inv; cy = sy * inv; cz = sz * inv;
+                c_group = group;
             }
-            const int gchunk = t0 / C + c;
+            float qx[Q], qy[Q], qz[Q];  // -2 (q - c)
+            float best[Q], second[Q];
+            int bchunk[Q];
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
-                const float v = cm[i];
-                second[i] = fminf(second[i], fmaxf(best[i], v));
-                const bool lt = v < best[i];
-                best[i] = fminf(best[i], v);
-                bchunk[i] = lt ? gchunk : bchunk[i];
+                qx[i] = -2.0f * (sq[(bl * 3 + 0) * QB + i * 32 + lane] - cx);
+                qy[i] = -2.0f * (sq[(bl * 3 + 1) * QB + i * 32 + lane] - cy);
+                qz[i] = -2.0f * (sq[(bl * 3 + 2) * QB + i * 32 + lane] - cz);
+                best[i] = kBig; second[i] = kBig; bchunk[i] = 0;
+            }
+            float blk_wmax = 0.f;
+            int blk_bad = 0;
+            const bool vec_ok = (tps == 3) && (tcs == 1) && ((reinterpret_cast<unsigned long long>(tb) & 15ull) == 0ull);
+
+            for (int t0 = 0; t0 < nt; t0 += TM) {
+                const int cnt = min(TM, nt - t0);
+                const int nchunks = (cnt + C - 1) / C;
+                if (!(res_group == group && res_t0 == t0)) {
+                    // ---- (re)load the tile: everybody must be done with the previous one
+                    __syncthreads();
+                    if (tid == 0) { s_tile_wmax = 0.f; s_tile_bad = 0; }
+                    float wmax = 0.f;
+                    int bad = 0;
+                    if (vec_ok && (cnt & 7) == 0) {
+                        // AoS fast path: 6 x LDG.128 = 24 floats = 8 whole points per thread and round
+                        for (int g8 = tid; g8 * 8 < cnt; g8 += kThreads) {
+                            const float4 *src = reinterpret_cast<const float4 *>(tb + (long long)t0 * 3) + g8 * 6;
+                            float f[24];
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                const float4 v = __ldg(src + i);
+                                f[4 * i + 0] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+                            }
+                            float xs[8], ys[8], zs[8], ws[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                xs[i] = f[3 * i + 0] - cx;
+                                ys[i] = f[3 * i + 1] - cy;
+                                zs[i] = f[3 * i + 2] - cz;
+                                ws[i] = __fmaf_rn(zs[i], zs[i], __fmaf_rn(xs[i], xs[i], ys[i] * ys[i]));
+                                bad |= !(ws[i] < kLimit);
+                                wmax = fmaxf(wmax, ws[i]);
+                            }
+                            float4 *dX = reinterpret_cast<float4 *>(sX) + g8 * 2, *dY = reinterpret_cast<float4 *>(sY) + g8 * 2;
+                            float4 *dZ = reinterpret_cast<float4 *>(sZ) + g8 * 2, *dW = reinterpret_cast<float4 *>(sW) + g8 * 2;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                dX[h] = make_float4(xs[4 * h], xs[4 * h + 1], xs[4 * h + 2], xs[4 * h + 3]);
+                                dY[h] = make_float4(ys[4 * h], ys[4 * h + 1], ys[4 * h + 2], ys[4 * h + 3]);
+                                dZ[h] = make_float4(zs[4 * h], zs[4 * h + 1], zs[4 * h + 2], zs[4 * h + 3]);
+                                dW[h] = make_float4(ws[4 * h], ws[4 * h + 1], ws[4 * h + 2], ws[4 * h + 3]);
+                            }
+                        }
+                        for (int k = cnt + tid; k < nchunks * C; k += kThreads) { sX[k] = 0.f; sY[k] = 0.f; sZ[k] = 0.f; sW[k] = kBig; }
+                    } else {
+                        // generic strides / ragged tile: 4 points per thread per round, loads issued before use
+                        for (int k0 = tid; k0 < nchunks * C; k0 += 4 * kThreads) {
+                            float lx[4], ly[4], lz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int k = k0 + i * kThreads;
+                                const float *tp = tb + (long long)(t0 + (k < cnt ? k : 0)) * tps;
+                                lx[i] = __ldg(tp); ly[i] = __ldg(tp + tcs); lz[i] = __ldg(tp + 2 * tcs);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int k = k0 + i * kThreads;
+                                if (k < nchunks * C) {
+                                    float x = 0.f, y = 0.f, z = 0.f, w = kBig;
+                                    if (k < cnt) {
+                                        x = lx[i] - cx; y = ly[i] - cy; z = lz[i] - cz;
+                                        w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
+                                        bad |= !(w < kLimit);
+                                        wmax = fmaxf(wmax, w);
+                                    }
+                                    sX[k] = x; sY[k] = y; sZ[k] = z; sW[k] = w;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+                        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+                    }
+                    __syncthreads();  // s_tile_* reset is visible; all tile stores are done
+                    if (lane == 0) {
+                        atomicMax(reinterpret_cast<int *>(&s_tile_wmax), __float_as_int(wmax));  // wmax >= 0: int order == float order
+                        if (bad) atomicOr(&s_tile_bad, 1);
+                    }
+                    __syncthreads();
+                    res_group = group; res_t0 = t0;
+                    res_wmax = s_tile_wmax; res_bad = s_tile_bad;
+                }
+                blk_wmax = fmaxf(blk_wmax, res_wmax);
+                blk_bad |= res_bad;
+
+                // software-pipelined over 4-target groups: the next group's four LDS.128 are issued before the
+                // current group's 24 FFMA2, also across chunk boundaries.  TM is a template constant so the
+                // four arrays are immediate offsets from one address register.
+                const float4 *T4 = reinterpret_cast<const float4 *>(sX);
+                constexpr int OY = TM / 4, OZ = 2 * (TM / 4), OW = 3 * (TM / 4);
+                int c = warp;
+                float4 X, Y, Z, W;
+                if (c < nchunks) {
+                    const float4 *g0 = T4 + c * (C / 4);
+                    X = g0[0]; Y = g0[OY]; Z = g0[OZ]; W = g0[OW];
+                }
+                while (c < nchunks) {
+                    float cm[Q];
+                    const int cn = c + kWarps;
+                    const float4 *gp = T4 + c * (C / 4);
+                    const float4 *gn = T4 + cn * (C / 4);
+#pragma unroll
+                    for (int g = 0; g < C / 4; ++g) {
+                        float4 Xn = X, Yn = Y, Zn = Z, Wn = W;
+                        if (g + 1 < C / 4) {
+                            Xn = gp[g + 1]; Yn = gp[g + 1 + OY]; Zn = gp[g + 1 + OZ]; Wn = gp[g + 1 + OW];
+                        } else if (cn < nchunks) {
+                            Xn = gn[0]; Yn = gn[OY]; Zn = gn[OZ]; Wn = gn[OW];
+                        }
+#pragma unroll
+                        for (int i = 0; i < Q; ++i) {
+                            float2 a01 = ffma2(qz[i], make_float2(Z.x, Z.y), make_float2(W.x, W.y));
+                            float2 a23 = ffma2(qz[i], make_float2(Z.z, Z.w), make_float2(W.z, W.w));
+                            a01 = ffma2(qy[i], make_float2(Y.x, Y.y), a01);
+                            a23 = ffma2(qy[i], make_float2(Y.z, Y.w), a23);
+                            a01 = ffma2(qx[i], make_float2(X.x, X.y), a01);
+                            a23 = ffma2(qx[i], make_float2(X.z, X.w), a23);
+                            if (g == 0) {
+                                cm[i] = fminf(fmin3(a01.x, a01.y, a23.x), a23.y);
+                            } else {
+                                cm[i] = fmin3(cm[i], a01.x, a01.y);
+                                cm[i] = fmin3(cm[i], a23.x, a23.y);
+                            }
+                        }
+                        X = Xn; Y = Yn; Z = Zn; W = Wn;
+                    }
+                    const int gchunk = t0 / C + c;
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) {
+                        const float v = cm[i];
+                        second[i] = fminf(second[i], fmaxf(best[i], v));
+                        const bool lt = v < best[i];
+                        best[i] = fminf(best[i], v);
+                        bchunk[i] = lt ? gchunk : bchunk[i];
+                    }
+                    c = cn;
+                }
+            }
+            // ---- park this warp's partial results for block bl (distinct slots per block: no barrier needed)
+            {
+                float *pb = part_best + (bl * kWarps + warp) * QB;
+                float *ps = part_second + (bl * kWarps + warp) * QB;
+                int *pc = part_chunk + (bl * kWarps + warp) * QB;
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    pb[i * 32 + lane] = best[i];
+                    ps[i * 32 + lane] = second[i];
+                    pc[i * 32 + lane] = bchunk[i];
+                }
+                if (tid == 0) {
+                    binfo[bl].cx = cx; binfo[bl].cy = cy; binfo[bl].cz = cz;
+                    binfo[bl].t2max = blk_wmax; binfo[bl].bad = blk_bad;
+                }
             }
         }
-    }
 
-    // ---- exchange the per-warp partial results through shared memory (tile buffers are free now)
-    __syncthreads();
-    float *pbest = sX;                            // [kWarps][QB]
-    float *psecond = sY;                          // [kWarps][QB]
-    int *pchunk = reinterpret_cast<int *>(sZ);    // [kWarps][QB]
-    int *fb_list = reinterpret_cast<int *>(sW);   // [QB]
-    static_assert(kWarps * QB <= kTile, "partial exchange must fit in one tile array");
+        // =========================== stage B: resolve the nb*128 queries of this flush group
+        __syncthreads();
+        for (int i = tid; i < nb * QB; i += kThreads) {   // a warp covers 32 consecutive queries of ONE block
+            const int bl = i / QB, ql = i - bl * QB;
+            const BlockInfo bi = binfo[bl];
+            const int cloud = bi.cloud;
+            const NNDirection &D = p.dir[bi.d];
+            const int j = D.q_begin + bi.qblock * QB + ql;
+            const bool live = j < D.q_begin + D.q_count;
+            float dres = 0.f;
+            bool done = false;
+            if (live) {
+                const int nt = D.nt;
+                const float *__restrict__ tb = D.t + (long long)cloud * D.t_bs;
+                const long long tps = D.t_ps, tcs = D.t_cs;
+                float b1 = kBig, b2 = kBig;
+                int bc = 0;
 #pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        pbest[warp * QB + i * 32 + lane] = best[i];
-        psecond[warp * QB + i * 32 + lane] = second[i];
-        pchunk[warp * QB + i * 32 + lane] = bchunk[i];
-    }
+                for (int w = 0; w < kWarps; ++w) {
+                    const float v = part_best[(bl * kWarps + w) * QB + ql];
+                    b2 = fminf(b2, fminf(part_second[(bl * kWarps + w) * QB + ql], fmaxf(b1, v)));
+                    if (v < b1) { b1 = v; bc = part_chunk[(bl * kWarps + w) * QB + ql]; }
+                }
+                const float x1 = sq[(bl * 3 + 0) * QB + ql], y1 = sq[(bl * 3 + 1) * QB + ql], z1 = sq[(bl * 3 + 2) * QB + ql];
+                const float ux = x1 - bi.cx, uy = y1 - bi.cy, uz = z1 - bi.cz;
+                const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
+                // margin = 26u * min(S, S') with 15% slack (u = 2^-24; derivation in DESIGN.md):
+                //   S  = (|q-c| + max|t-c|)^2 bounds every target,
+                //   S' = (2|q-c| + rho)^2 bounds the targets that can compete (within rho of the query).
+                const float qn = sqrtf(qq);
+                const float r = qn + sqrtf(bi.t2max);
+                const float S = r * r;
+                const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 2.4e-6f * S);
+                const float r2 = 2.0f * qn + rho;
+                const float Seff = fminf(S, r2 * r2);
+                const float margin = __fmaf_rn(Seff, 1.8e-6f, 1e-36f);
+                const bool ok = !bi.bad && (S < 4.0f * kLimit) && (b2 > b1 + margin);
+                if (ok) {
+                    const int k0 = bc * C;
+                    const int k1 = min(k0 + C, nt);
+                    float dv[C];
+                    if (tps == 3 && tcs == 1 && k1 - k0 == C && ((reinterpret_cast<unsigned long long>(tb) & 15ull) == 0ull)) {
+                        // AoS, 16-byte aligned chunk (16 points = 192 B): 12 x LDG.128 in flight at once
+                        const float4 *src = reinterpret_cast<const float4 *>(tb + (long long)k0 * 3);
+                        float f[3 * C];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-    }
-    if (lane == 0) { s_wmax[warp] = wmax; s_bad[warp] = bad; }
-    if (tid == 0) s_nfb = 0;
-    __syncthreads();
-    const float t2max = fmaxf(fmaxf(s_wmax[0], s_wmax[1]), fmaxf(s_wmax[2], s_wmax[3]));
-    const bool cta_bad = (s_bad[0] | s_bad[1] | s_bad[2] | s_bad[3]) != 0;
-    const float tmax = sqrtf(t2max);
-
-    float loc_sum = 0.f;
-    int loc_cnt = 0;
-    float *dist_out = D.dist + (long long)cloud * D.nq;
-    int *idx_out = D.idx + (long long)cloud * D.nq;
-
-    for (int ql = tid; ql < QB; ql += kThreads) {
-        const int j = q0 + ql;
-        if (j >= q_end) continue;
-        float b1 = kBig, b2 = kBig;
-        int bc = 0;
+                        for (int u = 0; u < 3 * C / 4; ++u) {
+                            const float4 v = __ldg(src + u);
+                            f[4 * u] = v.x; f[4 * u + 1] = v.y; f[4 * u + 2] = v.z; f[4 * u + 3] = v.w;
+                        }
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const float v = pbest[w * QB + ql];
-            b2 = fminf(b2, fminf(psecond[w * QB + ql], fmaxf(b1, v)));
-            if (v < b1) { b1 = v; bc = pchunk[w * QB + ql]; }
-        }
-        const float x1 = __ldg(qb + j * qps), y1 = __ldg(qb + j * qps + qcs), z1 = __ldg(qb + j * qps + 2 * qcs);
-        const float ux = x1 - cx, uy = y1 - cy, uz = z1 - cz;
-        const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
-        const float r = sqrtf(qq) + tmax;
-        const float S = r * r;
-        const float margin = __fmaf_rn(S, 3.814697265625e-6f /* 2^-18 */, 1e-36f);
-        const bool ok = !cta_bad && (S < 4.0f * kLimit) && (b2 > b1 + margin);
-        if (ok) {
-            const int k0 = bc * C;
-            const int k1 = min(k0 + C, nt);
-            const float *tp = tb + (long long)k0 * tps;
-            float dbest = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
-            int ibest = k0;
-            for (int k = k0 + 1; k < k1; ++k) {
-                tp += tps;
-                const float d = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
-                if (d < dbest) { dbest = d; ibest = k; }
+                        for (int u = 0; u < C; ++u) dv[u] = sqdist_exact(f[3 * u] - x1, f[3 * u + 1] - y1, f[3 * u + 2] - z1);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < C; ++u) dv[u] = exact_d(tb, tps, tcs, min(k0 + u, k1 - 1), x1, y1, z1);
+                    }
+                    float dbest = dv[0];
+                    int ibest = k0;
+#pragma unroll
+                    for (int u = 1; u < C; ++u) {
+                        if (k0 + u < k1 && dv[u] < dbest) { dbest = dv[u]; ibest = k0 + u; }
+                    }
+                    D.dist[(long long)cloud * D.nq + j] = dbest;
+                    D.idx[(long long)cloud * D.nq + j] = ibest;
+                    dres = dbest;
+                    done = true;
+                } else {
+                    fb_list[atomicAdd(&s_nfb, 1)] = i;
+                }
             }
-            dist_out[j] = dbest;
-            idx_out[j] = ibest;
-            loc_sum += dbest;
-            loc_cnt += dbest < p.fs_thr;
-        } else {
-            fb_list[atomicAdd(&s_nfb, 1)] = ql;
-        }
-    }
-    __syncthreads();
-
-    // ---- exact full scan for the flagged queries (whole CTA per query).  Reference semantics incl. NaN:
-    // within a 512-target tile the first element is taken unconditionally and NaN never replaces or is
-    // replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
-    const int nfb = s_nfb;
-    for (int f = 0; f < nfb; ++f) {
-        const int ql = fb_list[f];
-        const int j = q0 + ql;
-        const float x1 = __ldg(qb + j * qps), y1 = __ldg(qb + j * qps + qcs), z1 = __ldg(qb + j * qps + 2 * qcs);
-        unsigned long long key = ~0ull;
-        for (int k = tid; k < nt; k += kThreads) {
-            const float *tp = tb + (long long)k * tps;
-            const float d = sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
-            const float *ts = tb + (long long)(k & ~(kRefTile - 1)) * tps;
-            const float dts = sqdist_exact(__ldg(ts) - x1, __ldg(ts + tcs) - y1, __ldg(ts + 2 * tcs) - z1);
-            if (!(d != d) && !(dts != dts)) {
-                const unsigned long long kk = pack_key(d, k);
-                key = kk < key ? kk : key;
+            if (p.sums != nullptr || p.fs_count != nullptr) {   // fused epilogues, one atomic per warp
+                float ws = done ? dres : 0.f;
+                int wc = (done && dres < p.fs_thr) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ws += __shfl_xor_sync(0xffffffffu, ws, o);
+                    wc += __shfl_xor_sync(0xffffffffu, wc, o);
+                }
+                if (lane == 0) {
+                    if (p.sums) atomicAdd(p.sums + cloud * 2 + D.slot, ws);
+                    if (p.fs_count && wc) atomicAdd(p.fs_count + cloud * 2 + D.slot, wc);
+                }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = shfl_xor_u64(key, o);
-            key = other < key ? other : key;
-        }
-        if (lane == 0) s_key[warp] = key;
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long kmin = s_key[0];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) kmin = s_key[w] < kmin ? s_key[w] : kmin;
-            const float d0 = sqdist_exact(__ldg(tb) - x1, __ldg(tb + tcs) - y1, __ldg(tb + 2 * tcs) - z1);
-            float dres;
-            int ires;
-            if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
-            else { dres = __uint_as_float((unsigned int)(kmin >> 32)); ires = (int)(kmin & 0xffffffffu); }
-            dist_out[j] = dres;
-            idx_out[j] = ires;
-            loc_sum += dres;
-            loc_cnt += dres < p.fs_thr;
-        }
-        __syncthreads();
-    }
-    if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries, (unsigned long long)nfb);
 
-    // ---- fused epilogues: per-cloud loss sums (loss/loss.py:36) and F-score counts (loss/loss_.py:132-133)
-    if (p.sums != nullptr || p.fs_count != nullptr) {
+        // ---- exact full scan for the flagged queries, the whole CTA per query.  Reference semantics incl. NaN:
+        // within a 512-target tile the first element is taken unconditionally and NaN never replaces or is
+        // replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+        const int nfb = s_nfb;
+        for (int f = 0; f < nfb; ++f) {   // 4 independent targets per thread and round
+            const int i = fb_list[f];
+            const int bl = i / QB, ql = i - bl * QB;
+            const BlockInfo bi = binfo[bl];
+            const int cloud = bi.cloud;
+            const NNDirection &D = p.dir[bi.d];
+            const int j = D.q_begin + bi.qblock * QB + ql;
+            const int nt = D.nt;
+            const float *__restrict__ tb = D.t + (long long)cloud * D.t_bs;
+            const long long tps = D.t_ps, tcs = D.t_cs;
+            const float x1 = sq[(bl * 3 + 0) * QB + ql], y1 = sq[(bl * 3 + 1) * QB + ql], z1 = sq[(bl * 3 + 2) * QB + ql];
+            const bool nan_possible = bi.bad || !(fabsf(x1) < 1e18f) || !(fabsf(y1) < 1e18f) || !(fabsf(z1) < 1e18f);
+            unsigned long long key = ~0ull;
+            for (int kb = tid; kb < nt; kb += 4 * kThreads) {
+                float dd[4], dts[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            loc_sum += __shfl_xor_sync(0xffffffffu, loc_sum, o);
-            loc_cnt += __shfl_xor_sync(0xffffffffu, loc_cnt, o);
+                for (int u = 0; u < 4; ++u) {
+                    const int k = min(kb + u * kThreads, nt - 1);
+                    dd[u] = exact_d(tb, tps, tcs, k, x1, y1, z1);
+                    dts[u] = nan_possible ? exact_d(tb, tps, tcs, k & ~(kRefTile - 1), x1, y1, z1) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = kb + u * kThreads;
+                    if (k < nt && !(dd[u] != dd[u]) && !(dts[u] != dts[u])) {
+                        const unsigned long long kk = pack_key(dd[u], k);
+                        key = kk < key ? kk : key;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = shfl_xor_u64(key, o);
+                key = other < key ? other : key;
+            }
+            if (lane == 0) s_key[warp] = key;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long kmin = s_key[0];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) kmin = s_key[w] < kmin ? s_key[w] : kmin;
+                const float d0 = exact_d(tb, tps, tcs, 0, x1, y1, z1);
+                float dres;
+                int ires;
+                if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
+                else { dres = __uint_as_float((unsigned int)(kmin >> 32)); ires = (int)(kmin & 0xffffffffu); }
+                D.dist[(long long)cloud * D.nq + j] = dres;
+                D.idx[(long long)cloud * D.nq + j] = ires;
+                if (p.sums) atomicAdd(p.sums + cloud * 2 + D.slot, dres);
+                if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + cloud * 2 + D.slot, 1);
+            }
+            __syncthreads();
         }
-        if (lane == 0) { s_sum[warp] = loc_sum; s_cnt[warp] = loc_cnt; }
-        __syncthreads();
-        if (tid == 0) {
-            if (p.sums) atomicAdd(p.sums + cloud * 2 + D.slot, (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]));
-            if (p.fs_count) atomicAdd(p.fs_count + cloud * 2 + D.slot, s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3]);
-        }
+        if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries, (unsigned long long)nfb);
+        __syncthreads();  // partial-result slots, staged queries and fb_list are reused by the next flush group
     }
 }
 
@@ -427,20 +562,23 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
 // ------------------------------------------------------------------------------------------------
 using namespace psd;
 
-static inline int pick_q(long long total_queries, int num_sms) {
-    // 4 queries per thread (128 per CTA) unless the problem is so large that the CTA count is
-    // irrelevant for balance; Q=8 halves the shared-memory reads per pair.
-    (void)total_queries; (void)num_sms;
-    return 4;
-}
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+static bool g_attr_set = false;
 
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
                                        float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
                                        int *fs_count, int q_begin, int q_count, cudaStream_t stream) {
     if (b <= 0 || n <= 0 || m <= 0) return cudaSuccess;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
     NNParams p;
-    const int Q = pick_q((long long)b * (n + m), 148);
-    const int QB = 32 * Q;
+    const int QB = kQB;
     auto fill = [&](NNDirection &D, const float *q, int nq, const float *t, int nt, float *dist, int *idx, int slot) {
         D.q = q; D.t = t; D.nq = nq; D.nt = nt; D.dist = dist; D.idx = idx; D.slot = slot;
         if (layout == 0) { D.q_ps = 3; D.q_cs = 1; D.t_ps = 3; D.t_cs = 1; }
@@ -455,12 +593,35 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     };
     fill(p.dir[0], xyz1, n, xyz2, m, dist1, idx1, 0);
     fill(p.dir[1], xyz2, m, xyz1, n, dist2, idx2, 1);
-    p.blocks_dir0 = b * p.dir[0].qblocks;
-    p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
     const long long blocks = (long long)b * (p.dir[0].qblocks + p.dir[1].qblocks);
     if (blocks == 0) return cudaSuccess;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    chamfer_nn_kernel<4><<<(unsigned int)blocks, kThreads, 0, stream>>>(p);
+    if (blocks > 0x3fffffffLL) return cudaErrorInvalidConfiguration;
+    p.blocks_dir0 = b * p.dir[0].qblocks;
+    p.total_blocks = (int)blocks;
+    p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
+    // persistent grid: one CTA per SM, each takes a contiguous range of 128-query blocks
+    const int grid = blocks < g_num_sms ? (int)blocks : g_num_sms;
+    const int per_cta = (int)((blocks + grid - 1) / grid);
+    int tile = 1024;
+    const int tmax = n > m ? n : m;
+    while (tile < tmax && tile < 4096) tile *= 2;
+    const size_t fixed = (size_t)tile * 16 + 2048;  // tile arrays + static shared memory + slack
+    const size_t per_block = (size_t)kPerBlockBytes;
+    int flush = (int)(((size_t)g_max_smem - fixed) / per_block);
+    if (flush > per_cta) flush = per_cta;
+    if (flush < 1) flush = 1;
+    p.tile = tile; p.flush = flush;
+    const size_t smem = (size_t)tile * 16 + (size_t)flush * per_block + 64;
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(chamfer_nn_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
+        if (e != cudaSuccess) return e;
+        g_attr_set = true;
+    }
+    if (tile == 1024) chamfer_nn_kernel<1024><<<grid, kThreads, smem, stream>>>(p);
+    else if (tile == 2048) chamfer_nn_kernel<2048><<<grid, kThreads, smem, stream>>>(p);
+    else chamfer_nn_kernel<4096><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

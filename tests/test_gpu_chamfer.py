@@ -167,3 +167,49 @@ def test_errors_are_loud(pkg, cuda):
     xd = torch.rand(2, 64, 3, device=cuda, dtype=torch.float64)
     with pytest.raises(RuntimeError):
         pkg.chamfer_3DDist()(xd, xd)
+
+
+def test_query_sharding_with_cuda_ops_emulated_ranks(pkg, oracle, cuda):
+    """The CUDA local operator of sharding.py, two 'ranks' run one after the other in this process (no
+    process group: the all_reduce is emulated by summing the disjoint slices)."""
+    from importlib import import_module
+    import psd_b200
+    sh = import_module(psd_b200.PKG_NAME + ".sharding")
+    x, y = make_clouds("uniform", 2, 1500, 900, seed=71)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    outs = [sh.chamfer_query_sharded(tx, ty, r, 2, threshold=1e-4, assemble=False) for r in range(2)]
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    got = [sum(o[k] for o in outs).cpu().numpy() for k in ("dist1", "dist2", "idx1", "idx2")]
+    assert_bit_equal(got, want, "query-sharded")
+    c1, c2 = oracle.fscore_counts(want[0], want[1], 1e-4)
+    assert (sum(o["counts"] for o in outs).cpu().numpy() == np.stack([c1, c2], 1)).all()
+    g1 = torch.rand(2, 1500, device=cuda); g2 = torch.rand(2, 900, device=cuda)
+    i1 = torch.from_numpy(want[2]).to(cuda); i2 = torch.from_numpy(want[3]).to(cuda)
+    parts = [sh.chamfer_backward_query_sharded(tx, ty, g1, g2, i1, i2, r, 2) for r in range(2)]
+    w1, w2 = oracle.chamfer_backward(x, y, g1.cpu().numpy(), g2.cpu().numpy(), want[2], want[3])
+    assert np.allclose((parts[0][0] + parts[1][0]).cpu().numpy(), w1, rtol=1e-5, atol=1e-6)
+    assert np.allclose((parts[0][1] + parts[1][1]).cpu().numpy(), w2, rtol=1e-5, atol=1e-6)
+
+
+def test_large_cloud_properties(pkg, oracle, cuda):
+    """BASELINE.json configs[4] scale (N=M=131072 is too slow for the CPU oracle): size-independent properties --
+    dist equals the exact distance along idx, no sampled target is closer, F-score counts match a recount,
+    and a 16k-query slice is bit-exact against the oracle."""
+    b, n = 1, 131072
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(b, n, 3, generator=g)
+    y = torch.rand(b, n, 3, generator=g)
+    tx, ty = x.to(cuda), y.to(cuda)
+    out = pkg.chamfer_fscore_fused(tx, ty, threshold=1e-4)
+    d1, i1 = out["dist1"], out["idx1"].long()
+    sel = torch.gather(ty, 1, i1.unsqueeze(-1).expand(-1, -1, 3))
+    diff = sel - tx
+    dd = torch.addcmul(torch.addcmul(diff[..., 1] * diff[..., 1], diff[..., 0], diff[..., 0]), diff[..., 2], diff[..., 2])
+    assert torch.allclose(dd, d1, rtol=1e-6, atol=0)
+    probe = ty[:, torch.randint(0, n, (64,), generator=g)]
+    pd = ((tx[:, :, None, :] - probe[:, None, :, :]) ** 2).sum(-1).min(2)[0]
+    assert bool((d1 <= pd * (1 + 1e-5)).all())
+    assert int(out["counts"][0, 0]) == int((d1 < 1e-4).sum()) and int(out["counts"][0, 1]) == int((out["dist2"] < 1e-4).sum())
+    # bit-exact slice against the oracle: first 2048 queries of direction 1 against all targets
+    wd, _, wi, _ = oracle.chamfer_forward(x[:, :2048].numpy(), y.numpy(), nthreads=16)
+    assert np.array_equal(d1[:, :2048].cpu().numpy(), wd) and np.array_equal(out["idx1"][:, :2048].cpu().numpy(), wi)

@@ -71,7 +71,11 @@ def test_emd_matches_reference_extension(pkg, oracle, cuda, ref, cfg):
     same = (rass == ass).all(1).cpu().numpy()
     print(f"clouds identical to the reference extension: {int(same.sum())}/{b}; oracle multi-winner events: {st['multi_winner']}")
     assert int((~same).sum()) <= max(st["multi_winner"], 0) + 2
-    ref_loss = float(torch.sqrt(rdist).mean(1).mean()); our_loss = float(torch.sqrt(dist).mean(1).mean())
-    assert abs(ref_loss - our_loss) <= 1e-5 * ref_loss * max(1, int((~same).sum())) + 1e-7
-    if same.all():
-        assert torch.equal(rdist, dist)
+    # clouds without a race in the reference: bit-identical distances
+    sm = torch.from_numpy(same).to(cuda)
+    assert torch.equal(rdist[sm], dist[sm])
+    # clouds where the reference's race picked another (equally valid) winner: the auction takes a different
+    # path from there on, so only the per-cloud loss is comparable -- both are eps-approximations of the same EMD
+    if (~sm).any():
+        rl = torch.sqrt(rdist[~sm]).mean(1); ol = torch.sqrt(dist[~sm]).mean(1)
+        assert float(((rl - ol).abs() / rl).max()) <= 2e-2

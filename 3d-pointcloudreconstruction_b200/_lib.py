@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsd_b200.so")
+LIB_PATH = os.environ.get("PSD_B200_LIB") or os.path.join(_HERE, "libpsd_b200.so")  # env override: A/B builds of the same ABI
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -34,14 +34,15 @@ lib.psd_emd_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp]
 lib.psd_chamfer_forward_host.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp]
 lib.psd_fp32_fma_peak.argtypes = [_cf, ctypes.POINTER(_cf), _vp]
 lib.psd_chamfer_stats.argtypes = [ctypes.POINTER(ctypes.c_longlong), _ci]
+lib.psd_chamfer_nn_variant.argtypes = [_ci]
 for _n in ("psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward", "psd_emd_forward",
            "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward", "psd_chamfer_forward_host",
-           "psd_fp32_fma_peak", "psd_chamfer_stats"):
+           "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant"):
     getattr(lib, _n).restype = _ci
 
 EXPORTS = ("psd_version", "psd_last_error", "psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward",
            "psd_emd_forward", "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward",
-           "psd_chamfer_forward_host", "psd_fp32_fma_peak", "psd_chamfer_stats")
+           "psd_chamfer_forward_host", "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant")
 
 
 def last_error() -> str:

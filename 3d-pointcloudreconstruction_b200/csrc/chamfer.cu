@@ -20,43 +20,13 @@
 //     order with strict '<'.  Otherwise (near-ties, duplicated points, non-finite input) the query takes
 //     an exact full scan that also reproduces the reference's NaN/512-tile semantics.
 //   => dist/idx are always produced by the exact formula; the filter only decides where to look.
-#include "psd_common.cuh"
+#include "chamfer_nn.cuh"
 
 namespace psd {
 
 constexpr int kWarps = 16;        // one persistent CTA per SM: 4 warps on each of the four sub-partitions
 constexpr int kThreads = kWarps * 32;
-constexpr int kQ = 4;             // queries per lane
-constexpr int kQB = 32 * kQ;      // queries per block (every warp of the CTA holds the same 128 queries)
-constexpr int kChunk = 16;        // targets per filter chunk
-constexpr float kBig = 1e30f;     // padding value for w[]; larger than any admissible filter value
-constexpr float kLimit = 1e18f;   // |t-c|^2, |q-c|^2 above this (or NaN) route the query to the exact scan
-constexpr int kRefTile = 512;     // the reference's tile (chamfer3D.cu:13), only observable with NaN inputs
 constexpr int kPartBytes = kWarps * kQB * 12;  // per-block partial results: (best, second, chunk) per warp and query
-
-struct NNDirection {
-    const float *q;      // query cloud base
-    const float *t;      // target cloud base
-    long long q_ps, q_cs, q_bs;  // query strides in floats: point, component, batch
-    long long t_ps, t_cs, t_bs;
-    float *dist;         // [B, nq]
-    int *idx;            // [B, nq]
-    int nq, nt;
-    int q_begin, q_count;  // query slice handled by this launch
-    int qblocks;           // 128-query blocks per cloud for this direction
-    int slot;              // 0/1: column in sums[B,2] / fs_count[B,2]
-};
-
-struct NNParams {
-    NNDirection dir[2];
-    int blocks_dir0;    // blocks belonging to dir[0]
-    int total_blocks;
-    int tile;           // targets per shared-memory tile (multiple of 1024)
-    int flush;          // blocks whose partial results fit in shared memory between two resolve phases
-    float *sums;        // optional [B,2]
-    int *fs_count;      // optional [B,2]
-    float fs_thr;
-};
 
 __device__ unsigned long long g_fallback_queries = 0ull;
 
@@ -68,13 +38,6 @@ struct BlockInfo {      // per block of the current flush group (shared memory)
     int pad[3];
 };
 constexpr int kPerBlockBytes = kPartBytes + (int)sizeof(BlockInfo) + 3 * kQB * 4 + kQB * 4;  // + staged queries + fallback list
-
-// exact squared distance of query (x1,y1,z1) to target k of a cloud with generic strides
-__device__ __forceinline__ float exact_d(const float *__restrict__ tb, long long tps, long long tcs, int k, float x1,
-                                         float y1, float z1) {
-    const float *tp = tb + (long long)k * tps;
-    return sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
-}
 
 template <int TM>
 __global__ void __launch_bounds__(kThreads, 1) chamfer_nn_kernel(const NNParams p) {
@@ -565,6 +528,16 @@ using namespace psd;
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 static bool g_attr_set = false;
+static int g_nn_variant = 0;   // 0 = auto, 1 = shared-block kernel (this file), 2 = grouped kernel
+
+cudaError_t psd_launch_nn_grouped(const NNParams &p, int num_sms, cudaStream_t stream);   // chamfer_nn_grouped.cu
+cudaError_t psd_read_chamfer_stats_grouped(unsigned long long *fallback, int reset);
+
+int psd_set_nn_variant(int v) {
+    const int old = g_nn_variant;
+    if (v >= 0 && v <= 2) g_nn_variant = v;
+    return old;
+}
 
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
                                        float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
@@ -599,6 +572,13 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     p.blocks_dir0 = b * p.dir[0].qblocks;
     p.total_blocks = (int)blocks;
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
+    p.tile = 0; p.flush = 0;
+    // Launches that give every 4-warp group of every SM at least two blocks run the grouped kernel (resolve and
+    // tile staging overlap the filter); smaller launches keep all 16 warps of a CTA on one block (latency).
+    // Measured (tools/nn_variants.py): +4 % at B=64 N=2048, but -25..-35 % for N >= 8192 -> auto only for small clouds.
+    const bool grouped = g_nn_variant == 2 ||
+                         (g_nn_variant == 0 && blocks >= 2LL * 4 * g_num_sms && n <= 4096 && m <= 4096);
+    if (grouped) return psd_launch_nn_grouped(p, g_num_sms, stream);
     // persistent grid: one CTA per SM, each takes a contiguous range of 128-query blocks
     const int grid = blocks < g_num_sms ? (int)blocks : g_num_sms;
     const int per_cta = (int)((blocks + grid - 1) / grid);
@@ -645,6 +625,10 @@ cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {
     if (reset) {
         const unsigned long long z = 0;
         e = cudaMemcpyToSymbol(g_fallback_queries, &z, sizeof(z));
+        if (e != cudaSuccess) return e;
     }
+    unsigned long long fg = 0;
+    e = psd_read_chamfer_stats_grouped(&fg, reset);
+    *fallback += fg;
     return e;
 }

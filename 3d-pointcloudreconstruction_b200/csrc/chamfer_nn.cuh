@@ -1,0 +1,46 @@
+// chamfer_nn.cuh -- launch description shared by the two Chamfer NN forward kernels
+// (chamfer.cu: shared-block kernel for small launches; chamfer_nn_grouped.cu: grouped kernel).
+#pragma once
+#include "psd_common.cuh"
+
+namespace psd {
+
+constexpr int kQ = 4;             // queries per lane
+constexpr int kQB = 32 * kQ;      // queries per block (every warp of the CTA holds the same 128 queries)
+constexpr int kChunk = 16;        // targets per filter chunk
+constexpr float kBig = 1e30f;     // padding value for w[]; larger than any admissible filter value
+constexpr float kLimit = 1e18f;   // |t-c|^2, |q-c|^2 above this (or NaN) route the query to the exact scan
+constexpr int kRefTile = 512;     // the reference's tile (chamfer3D.cu:13), only observable with NaN inputs
+
+struct NNDirection {
+    const float *q;      // query cloud base
+    const float *t;      // target cloud base
+    long long q_ps, q_cs, q_bs;  // query strides in floats: point, component, batch
+    long long t_ps, t_cs, t_bs;
+    float *dist;         // [B, nq]
+    int *idx;            // [B, nq]
+    int nq, nt;
+    int q_begin, q_count;  // query slice handled by this launch
+    int qblocks;           // 128-query blocks per cloud for this direction
+    int slot;              // 0/1: column in sums[B,2] / fs_count[B,2]
+};
+
+struct NNParams {
+    NNDirection dir[2];
+    int blocks_dir0;    // blocks belonging to dir[0]
+    int total_blocks;
+    int tile;           // targets per shared-memory tile (multiple of 1024)
+    int flush;          // blocks whose partial results fit in shared memory between two resolve phases
+    float *sums;        // optional [B,2]
+    int *fs_count;      // optional [B,2]
+    float fs_thr;
+};
+
+// exact squared distance of query (x1,y1,z1) to target k of a cloud with generic strides
+__device__ __forceinline__ float exact_d(const float *__restrict__ tb, long long tps, long long tcs, int k, float x1,
+                                         float y1, float z1) {
+    const float *tp = tb + (long long)k * tps;
+    return sqdist_exact(__ldg(tp) - x1, __ldg(tp + tcs) - y1, __ldg(tp + 2 * tcs) - z1);
+}
+
+}  // namespace psd

@@ -13,6 +13,7 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
                                         int b, int n, int m, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
+int psd_set_nn_variant(int v);
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                                    float *price, int *assignment_inv, int *bid, float *bid_increments,
                                    float *max_increments, float eps, int iters, int force_cluster, int fresh,
@@ -114,6 +115,8 @@ int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const
                      int b, int n, void *stream) {
     return finish("psd_emd_backward", psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, (cudaStream_t)stream));
 }
+
+int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }
 
 int psd_chamfer_stats(long long *out_host2, int reset) {
     unsigned long long fb = 0;

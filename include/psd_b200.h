@@ -121,6 +121,11 @@ int psd_fp32_fma_peak(float ms_target, float *tflops, void *stream);
  * out[0] = queries resolved by the filtered path, out[1] = queries that took the exact full scan. */
 int psd_chamfer_stats(long long *out_host2, int reset);
 
+/* Test/measurement hook: choose the chamfer NN forward kernel.  0 = automatic (default: the grouped kernel for
+ * launches of >= 8 blocks of 128 queries per SM, the shared-block kernel below that), 1 = shared-block kernel,
+ * 2 = grouped kernel.  Both produce identical results.  Returns the previous setting. */
+int psd_chamfer_nn_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

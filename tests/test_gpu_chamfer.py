@@ -8,6 +8,15 @@ from conftest import make_clouds
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["shared_block", "grouped"], autouse=True)
+def nn_variant(request, pkg):
+    """Every test of this file runs against both NN forward kernels (psd_chamfer_nn_variant): the shared-block
+    kernel that small launches use and the grouped kernel that launches of >= 8 blocks per SM use."""
+    old = pkg._lib.lib.psd_chamfer_nn_variant(request.param)
+    yield request.param
+    pkg._lib.lib.psd_chamfer_nn_variant(old)
+
+
 def run_forward(pkg, dev, x, y):
     tx, ty = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
     d1, d2, i1, i2 = pkg.chamfer_3DDist()(tx, ty)

@@ -528,14 +528,23 @@ using namespace psd;
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 static bool g_attr_set = false;
-static int g_nn_variant = 0;   // 0 = auto, 1 = shared-block kernel (this file), 2 = grouped kernel
+static int g_nn_variant = 0;   // 0 = auto, 1 = shared-block kernel (this file), 2 = grouped kernel, 3 = tensor-core kernel
+static float *g_tc_dbg = nullptr;   // one-shot debug dump target of the tensor-core kernel (psd_debug_tc_filter)
+static int g_tc_dbg_ld = 0;
+
+bool psd_nn_tc_supported(const NNParams &p);                                               // chamfer_nn_tc.cu
+cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof);
+static long long *g_tc_prof = nullptr;
+void psd_set_tc_prof(long long *prof) { g_tc_prof = prof; }
+cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int *error, int reset);
+void psd_set_tc_debug(float *dbg, int ld) { g_tc_dbg = dbg; g_tc_dbg_ld = ld; }
 
 cudaError_t psd_launch_nn_grouped(const NNParams &p, int num_sms, cudaStream_t stream);   // chamfer_nn_grouped.cu
 cudaError_t psd_read_chamfer_stats_grouped(unsigned long long *fallback, int reset);
 
 int psd_set_nn_variant(int v) {
     const int old = g_nn_variant;
-    if (v >= 0 && v <= 2) g_nn_variant = v;
+    if (v >= 0 && v <= 3) g_nn_variant = v;
     return old;
 }
 
@@ -573,6 +582,12 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     p.total_blocks = (int)blocks;
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
     p.tile = 0; p.flush = 0;
+    // Tensor-core filter (chamfer_nn_tc.cu) whenever both target clouds fit its resident B operand.
+    if (g_nn_variant == 3 && psd_nn_tc_supported(p)) {   // not yet the automatic choice: v1 is slower than the FFMA kernel
+        float *dbg = g_tc_dbg;
+        g_tc_dbg = nullptr;
+        return psd_launch_nn_tc(p, g_num_sms, stream, dbg, g_tc_dbg_ld, g_tc_prof);
+    }
     // Launches that give every 4-warp group of every SM at least two blocks run the grouped kernel (resolve and
     // tile staging overlap the filter); smaller launches keep all 16 warps of a CTA on one block (latency).
     // Measured (tools/nn_variants.py): +4 % at B=64 N=2048, but -25..-35 % for N >= 8192 -> auto only for small clouds.
@@ -630,5 +645,11 @@ cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {
     unsigned long long fg = 0;
     e = psd_read_chamfer_stats_grouped(&fg, reset);
     *fallback += fg;
+    if (e != cudaSuccess) return e;
+    int tc_err = 0;
+    fg = 0;
+    e = psd_read_chamfer_stats_tc(&fg, &tc_err, reset);
+    *fallback += fg;
+    if (e == cudaSuccess && tc_err) e = cudaErrorLaunchTimeout;   // an mbarrier wait of the tensor-core kernel timed out
     return e;
 }

@@ -14,6 +14,8 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
                                         int b, int n, int m, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
 int psd_set_nn_variant(int v);
+void psd_set_tc_debug(float *dbg, int ld);
+void psd_set_tc_prof(long long *prof);
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                                    float *price, int *assignment_inv, int *bid, float *bid_increments,
                                    float *max_increments, float eps, int iters, int force_cluster, int fresh,
@@ -117,6 +119,19 @@ int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const
 }
 
 int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }
+
+int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
+
+int psd_debug_tc_filter(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                        int *idx2, float *dump, int dump_ld, void *stream) {
+    const int old = psd_set_nn_variant(3);
+    psd_set_tc_debug(dump, dump_ld);
+    cudaError_t e = psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, 0, dist1, dist2, idx1, idx2, nullptr, 0.f, nullptr, 0,
+                                               -1, (cudaStream_t)stream);
+    psd_set_tc_debug(nullptr, 0);
+    psd_set_nn_variant(old);
+    return finish("psd_debug_tc_filter", e);
+}
 
 int psd_chamfer_stats(long long *out_host2, int reset) {
     unsigned long long fb = 0;

@@ -121,10 +121,20 @@ int psd_fp32_fma_peak(float ms_target, float *tflops, void *stream);
  * out[0] = queries resolved by the filtered path, out[1] = queries that took the exact full scan. */
 int psd_chamfer_stats(long long *out_host2, int reset);
 
-/* Test/measurement hook: choose the chamfer NN forward kernel.  0 = automatic (default: the grouped kernel for
- * launches of >= 8 blocks of 128 queries per SM, the shared-block kernel below that), 1 = shared-block kernel,
- * 2 = grouped kernel.  Both produce identical results.  Returns the previous setting. */
+/* Test/measurement hook: choose the chamfer NN forward kernel.  0 = automatic (default: the tensor-core kernel when
+ * both clouds have <= 2048 points, else the FFMA kernels), 1 = shared-block FFMA kernel, 2 = grouped FFMA kernel,
+ * 3 = tensor-core (tcgen05) kernel.  All produce identical results.  Returns the previous setting. */
 int psd_chamfer_nn_variant(int variant);
+
+/* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
+ * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a
+ * unit is a block of 128 queries in launch order (direction 1 blocks first).  dump_ld >= n and m rounded up to 128. */
+int psd_debug_tc_filter(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
+                        int *idx2, float *dump, int dump_ld, void *stream);
+
+/* Phase clocks of the tensor-core kernel (tools/tc_phase_clocks.py): while prof_dev is non-NULL every launch of that
+ * kernel runs its instrumented build and writes 64 clock64 slots per CTA to prof_dev[148*64].  NULL switches it off. */
+int psd_debug_tc_prof(long long *prof_dev);
 
 #ifdef __cplusplus
 }

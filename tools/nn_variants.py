@@ -15,6 +15,7 @@ import psd_b200
 pkg = psd_b200.load()
 L = pkg._lib.lib
 dev = torch.device("cuda:0")
+VARIANTS = [int(v) for v in os.environ.get("NN_VARIANTS", "1,3").split(",")]
 
 
 def time_variant(variant, xs, ys, outs, reps):
@@ -54,16 +55,17 @@ def main():
         xs = [torch.rand(b, n, 3, generator=g).to(dev) for _ in range(pool)]
         ys = [torch.rand(b, m, 3, generator=g).to(dev) for _ in range(pool)]
         res = {}
-        for v in (1, 2):
+        for v in VARIANTS:
             outs = [(torch.empty(b, n, device=dev), torch.empty(b, m, device=dev),
                      torch.empty(b, n, device=dev, dtype=torch.int32), torch.empty(b, m, device=dev, dtype=torch.int32))
                     for _ in range(pool)]
             us = time_variant(v, xs, ys, outs, reps)
             torch.cuda.synchronize()
             res[v] = (us, outs)
-        same = all(torch.equal(a, b_) for oa, ob in zip(res[1][1], res[2][1]) for a, b_ in zip(oa, ob))
+        same = all(torch.equal(a, b_) for oa, ob in zip(res[VARIANTS[0]][1], res[VARIANTS[-1]][1]) for a, b_ in zip(oa, ob))
         line = f"B={b} N={n} M={m}: "
-        for v, name in ((1, "shared-block"), (2, "grouped")):
+        for v in VARIANTS:
+            name = {1: "shared-block", 2: "grouped", 3: "tensor-core"}[v]
             us = res[v][0]
             line += f"{name} {us:9.1f} us ({8 * pairs / (us * 1e-6) / 1e12:5.1f} TFLOP/s-alg)  "
         print(line + f"identical={same}", flush=True)

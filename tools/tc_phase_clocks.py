@@ -1,0 +1,63 @@
+"""Phase clocks of the tensor-core chamfer NN kernel (csrc/chamfer_nn_tc.cu): where do a CTA's cycles go?
+
+Runs a few warm launches, then one instrumented launch (psd_debug_tc_prof) and prints, averaged over the CTAs,
+the clock64 deltas between the stamps of consumer thread 0 and the wait totals of the MMA warp.
+
+    python tools/tc_phase_clocks.py [B N M]
+"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import psd_b200
+
+pkg = psd_b200.load()
+L = pkg._lib.lib
+dev = torch.device("cuda:0")
+b, n, m = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (32, 2048, 2048)
+g = torch.Generator().manual_seed(3)
+x = torch.rand(b, n, 3, generator=g).to(dev)
+y = torch.rand(b, m, 3, generator=g).to(dev)
+out = (torch.empty(b, n, device=dev), torch.empty(b, m, device=dev),
+       torch.empty(b, n, device=dev, dtype=torch.int32), torch.empty(b, m, device=dev, dtype=torch.int32))
+L.psd_chamfer_nn_variant(3)
+prof = torch.zeros(148 * 64, dtype=torch.int64, device=dev)
+L.psd_debug_tc_prof(ctypes.c_void_p(prof.data_ptr()))
+for _ in range(5):
+    prof.zero_()
+    assert pkg.chamfer_3D.forward(x, y, *out) == 1
+torch.cuda.synchronize()
+L.psd_debug_tc_prof(None)
+P = prof.cpu().numpy().reshape(148, 64).astype(np.float64)
+act = P[:, 0] > 0
+P = P[act]
+print(f"B={b} N={n} M={m}: {act.sum()} CTAs")
+t0 = P[:, 0]
+print(f"  setup (barrier init, TMEM alloc)        {np.mean(P[:, 1] - t0):9.0f}")
+print(f"  stage unit 0 (B + A operands)           {np.mean(P[:, 2] - P[:, 1]):9.0f}")
+prev = P[:, 2]
+names = ["scan end", "S1 (all consumed)", "S2 (next staged)", "resolve end", "S3", "fallback end"]
+for u in range(8):
+    base = 8 + u * 6
+    have = P[:, base] > 0
+    if not have.any():
+        break
+    line = f"  unit {u} ({have.sum():3d} CTAs):"
+    last = prev[have]
+    for i, nm in enumerate(names):
+        cur = P[have, base + i]
+        line += f"  {nm} +{np.mean(cur - last):7.0f}"
+        last = cur
+    print(line)
+    prev = P[:, base + 5].copy()
+    prev[~have] = P[~have, 2]
+end = P[:, 8:56].max(axis=1)
+print(f"  consumer thread 0 total                 {np.mean(end - t0):9.0f}  (max {np.max(end - t0):.0f})")
+print(f"  consumer warp 0 waiting on full barriers{np.mean(P[:, 59]):9.0f}")
+print(f"  MMA warp: waiting for operands          {np.mean(P[:, 56]):9.0f}")
+print(f"  MMA warp: waiting for empty buffers     {np.mean(P[:, 57]):9.0f}")
+print(f"  MMA warp: last issue at                 {np.mean(P[:, 58] - t0):9.0f}")

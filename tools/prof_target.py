@@ -6,6 +6,8 @@ import torch
 import psd_b200
 pkg = psd_b200.load()
 dev = torch.device("cuda:0")
+if os.environ.get("PSD_NN_VARIANT"):
+    pkg._lib.lib.psd_chamfer_nn_variant(int(os.environ["PSD_NN_VARIANT"]))
 B, N = 32, 2048
 torch.manual_seed(0)
 x = torch.rand(B, N, 3).to(dev); y = torch.rand(B, N, 3).to(dev)

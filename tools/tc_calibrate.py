@@ -1,7 +1,8 @@
 """Bring-up and calibration of the tensor-core chamfer NN kernel (csrc/chamfer_nn_tc.cu, variant 3).
 
 1. dumps the raw tensor-core filter values a_k through psd_debug_tc_filter and compares them with the same quantity in
-   float64: a_k = |t_k - q|^2 - |q - c|^2 (c = the kernel's frame centre: mean of 8 evenly spaced targets), reporting
+   float64: a_k = s^2 (|t_k - q|^2 - |q - c|^2) (c = the kernel's frame centre: mean of 8 evenly spaced targets, s = its
+   power-of-two scale), reporting
    max |error| / S with S = (|q-c| + max|t-c|)^2 in units of u = 2^-24 -- the constant the exactness margin relies on;
 2. checks dist/idx of variant 3 against the C oracle (bit-exact) on a few shapes;
 3. reports the fallback rate.
@@ -60,9 +61,14 @@ def calibrate(b, n, m, gen, name):
     for d, (qs, ts, qb, off) in enumerate(((xn, yn, qb1, 0), (yn, xn, qb2, b * qb1))):
         for cl in range(b):
             t = ts[cl]; q = qs[cl]
-            c = centre(t).astype(np.float64)
-            tc = t.astype(np.float64) - c
-            qc = q.astype(np.float64) - c
+            c32 = centre(t)
+            cmax = np.abs((t - c32).astype(np.float32)).max()
+            e = int((np.float32(cmax).view(np.uint32) >> 23) & 0xff)
+            e = min(max(e, 27), 227)
+            sc = 2.0 ** (126 - e) if cmax > 0 else 1.0      # the kernel's power-of-two scale: sc*cmax in [0.5, 1)
+            c = c32.astype(np.float64)
+            tc = (t.astype(np.float64) - c) * sc
+            qc = (q.astype(np.float64) - c) * sc
             a = (tc * tc).sum(1)[None, :] - 2.0 * qc @ tc.T           # [nq, nt]
             S = (np.sqrt((qc * qc).sum(1)) + np.sqrt((tc * tc).sum(1).max())) ** 2
             for blk in range(qb):

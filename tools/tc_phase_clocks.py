@@ -40,7 +40,7 @@ t0 = P[:, 0]
 print(f"  setup (barrier init, TMEM alloc)        {np.mean(P[:, 1] - t0):9.0f}")
 print(f"  stage unit 0 (B + A operands)           {np.mean(P[:, 2] - P[:, 1]):9.0f}")
 prev = P[:, 2]
-names = ["scan end", "S1 (all consumed)", "S2 (next staged)", "resolve end", "S3", "fallback end"]
+names = ["scan end", "S1 (all consumed)", "S2 (next staged)", "resolve end"]
 for u in range(8):
     base = 8 + u * 6
     have = P[:, base] > 0
@@ -53,9 +53,10 @@ for u in range(8):
         line += f"  {nm} +{np.mean(cur - last):7.0f}"
         last = cur
     print(line)
-    prev = P[:, base + 5].copy()
+    prev = P[:, base + 3].copy()
     prev[~have] = P[~have, 2]
-end = P[:, 8:56].max(axis=1)
+end = np.maximum(P[:, 8:56].max(axis=1), P[:, 4])
+print(f"  deferred exact scans                    {np.mean(P[:, 4] - P[:, 3]):9.0f}")
 print(f"  consumer thread 0 total                 {np.mean(end - t0):9.0f}  (max {np.max(end - t0):.0f})")
 print(f"  consumer warp 0 waiting on full barriers{np.mean(P[:, 59]):9.0f}")
 print(f"  MMA warp: waiting for operands          {np.mean(P[:, 56]):9.0f}")

@@ -12,47 +12,53 @@
 // (products of two 11-bit significands are exact in the fp32 accumulator; the dropped ql*tl terms and the split
 // residues are bounded by 3*2^-22 |q'||t'|).  Measured on B200 (tools/ubench_umma.cu): kind::f16 M128 N128 K16 issues
 // every 64 cycles, kind::tf32 K8 only every 96, independent of the shared-memory layout -- hence fp16 and one
-// instruction per tile instead of two TF32 K-slices.  Accumulators live in TMEM (4 buffers of 128 columns).  The 16
-// consumer warps read them back with tcgen05.ld.32x32b.x16 -- one thread owns one query row, so the running minimum
-// needs no cross-lane traffic -- and keep per 32-target chunk (best chunk minimum, its chunk id, second best) exactly
-// like the FFMA kernel: 15 FMNMX3 + 6 ALU ops per 32 pairs instead of 96 FFMA + 16 FMNMX3.
+// instruction per tile.  Accumulators live in TMEM (4 buffers of 128 columns).
 //
-// CTA = one per SM, persistent: warps 0-15 consumers (warp w: TMEM lanes 32*(w%4).., buffer w/4), warp 16 issues
-// the MMAs.  Per unit (128 queries of one cloud/direction): raw queries/targets arrive by cp.async one unit ahead;
-// consumers build the B operand (once per cloud) and the A operand in shared memory (K-major, no swizzle: 8-row x
-// 16-byte core matrices), signal the MMA warp, scan the tiles as their TMEM buffers fill (full/empty mbarriers,
-// tcgen05.commit), park their partial results, stage the NEXT unit, and only then resolve the current one (merge,
-// margin test, exact rescan of the best chunk from the raw targets in shared memory, fused loss-sum / F-score
-// epilogue).  The few queries that fail the margin test are deferred to a per-CTA list and take an exact full scan,
-// one warp per query, at the end.
+// One persistent CTA per SM, three concurrent roles (no CTA-wide barrier in the steady state):
+//   * warps 0-7   SCANNERS: warp w reads TMEM lanes 32*(w%4).. (one thread = one query row, so the running minimum
+//                 needs no cross-lane traffic) of the tiles of column group w/4 with tcgen05.ld.32x32b.x32, double
+//                 buffered, and keeps per 32-target chunk (best chunk minimum, its chunk id, second best): 16 min
+//                 instructions + 6 ALU ops per 32 pairs instead of 96 FFMA + 16 FMNMX3 in the FFMA kernel.
+//   * warp  8     MMA issuer: waits for operands (ready mbarrier) and a free TMEM buffer (empty mbarrier), issues one
+//                 tcgen05.mma per tile and commits it to the buffer's full mbarrier.
+//   * warps 9-15  HELPERS: stage the operands two units ahead (raw coordinates -> scaled split fp16, K-major core
+//                 matrices, double-buffered A and B), and resolve the unit the scanners just finished: merge the
+//                 partial results, margin test, exact rescan of the best chunk from raw targets kept in shared
+//                 memory, fused loss-sum / F-score epilogue.  Queries that fail the margin test go to a per-CTA
+//                 list and take an exact full scan, one warp per query, by all warps at the end.
+// A unit is a block of 128 queries of one cloud/direction; a CTA owns a contiguous range of units.
 #include <cuda_fp16.h>
 #include "chamfer_nn.cuh"
 
 namespace psd {
 namespace tc {
 
-constexpr int kConsWarps = 16;
-constexpr int kConsThreads = kConsWarps * 32;
-constexpr int kThreadsTC = kConsThreads + 32;   // + the MMA warp
+constexpr int kScanWarps = 8;
+constexpr int kMmaWarp = kScanWarps;            // warp index of the MMA issuer
+constexpr int kHelpWarps = 7;                   // 16 warps in all: 4 per sub-partition, 128 registers per thread
+constexpr int kHelpThreads = kHelpWarps * 32;
+constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
+constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 512
 constexpr int kTileN = 128;                     // targets per MMA tile = TMEM buffer width (columns)
 constexpr int kBufs = 4;                        // TMEM buffers: 4 x 128 columns = all 512
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
-constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact); real filter values are < 3 + 2*1e4*1.8
+constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value
 constexpr float kQMax = 4096.0f;                // scaled |q-c| above this sends the query to the exact scan: keeps |a| <= 3 + 3.5*kQMax < kPadW
 
 // shared-memory carve-up (bytes)
-constexpr int kOffB = 0;                                  // [kMaxT/8][2][8][16 B]
-constexpr int kOffA = kOffB + kMaxT * 32;                 // [16][2][8][16 B]
-constexpr int kOffRaw = kOffA + kQB * 32;                 // [2][3][kMaxT] raw target coordinates (SoA), by cloud parity
-constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][4 column groups][3][128]
-constexpr int kOffSq = kOffPart + 2 * 4 * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
+constexpr int kOffB = 0;                                  // [2][kMaxT/8][2][8][16 B]
+constexpr int kOffA = kOffB + 2 * kMaxT * 32;             // [2][16][2][8][16 B]
+constexpr int kOffRaw = kOffA + 2 * kQB * 32;             // [2][3][kMaxT] raw target coordinates (SoA), by B buffer
+constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][2 column groups][3][128]
+constexpr int kOffSq = kOffPart + 2 * 2 * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
 constexpr int kFbCap = 512;                               // deferred exact-scan list (entries: unit << 8 | query)
 constexpr int kOffFb = kOffSq + 3 * 3 * kQB * 4;
-constexpr int kOffStat = kOffFb + kFbCap * 4;             // [16] wmax, [16] bad, [16] cmax
-constexpr int kOffBar = kOffStat + 3 * kConsWarps * 4;    // 9 mbarriers
+constexpr int kOffStat = kOffFb + kFbCap * 4;             // [8] wmax, [8] bad, [8] cmax
+constexpr int kOffBar = kOffStat + 3 * 8 * 4;             // 12 mbarriers (8-byte aligned)
 constexpr int kOffMisc = kOffBar + 16 * 8;                // tmem base, nfb, abort
 constexpr int kSmemTC = kOffMisc + 64;
+static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8, "shared-memory carve-up alignment");
 
 __device__ unsigned long long g_fallback_queries_tc = 0ull;
 __device__ int g_tc_error = 0;
@@ -93,7 +99,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsThreads) : "memory"); }
+__device__ __forceinline__ void help_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kHelpThreads) : "memory"); }
 // x -> (hi, lo) fp16 pair with hi + lo = x up to 2^-22 |x| (or 2^-25 absolute in the subnormal range)
 __device__ __forceinline__ void split_h(float x, unsigned short &hi, unsigned short &lo) {
     const __half h = __float2half_rn(x);
@@ -116,30 +122,32 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// one tcgen05.ld of 16 consecutive columns of this thread's TMEM lane; completes at the next tmem_wait()
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// two tcgen05.ld of 32 consecutive columns each of this thread's TMEM lane (a, then b) AND the wait for them in ONE
+// asm statement: the destination registers are written asynchronously until tcgen05.wait::ld, so the compiler must
+// never see them as defined in between (a spill or a move there would read stale data).
+__device__ __forceinline__ void tmem_ld64_wait(uint32_t taddr, uint32_t (&a)[32], uint32_t (&b)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31]),
+          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
+        : "r"(taddr), "r"(taddr + 32u)
+        : "memory");
 }
-// wait for the outstanding tcgen05.ld; the registers are in/out operands so that no use of them can be scheduled above
-__device__ __forceinline__ void tmem_wait(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :: "memory");
-}
-// minimum of 16 filter values: 7 FMNMX3 + 1 FMNMX
-__device__ __forceinline__ float min16(const uint32_t (&r)[16]) {
-    float a = fmin3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
-    float b = fmin3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
-    float c = fmin3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
-    float d = fmin3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
-    a = fmin3(a, __uint_as_float(r[12]), __uint_as_float(r[13]));
-    b = fmin3(b, __uint_as_float(r[14]), __uint_as_float(r[15]));
-    return fminf(fmin3(a, b, c), d);
+// minimum of 32 filter values: 15 FMNMX3 + 1 FMNMX, four independent chains
+__device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
+    float m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = fmin3(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]), __uint_as_float(r[8 * i + 2]));
+        m[i] = fmin3(m[i], __uint_as_float(r[8 * i + 3]), __uint_as_float(r[8 * i + 4]));
+        m[i] = fmin3(m[i], __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]));
+    }
+    float v = fmin3(m[0], m[1], m[2]);
+    v = fmin3(v, m[3], __uint_as_float(r[7]));
+    v = fmin3(v, __uint_as_float(r[15]), __uint_as_float(r[23]));
+    return fminf(v, __uint_as_float(r[31]));
 }
 
 struct Unit {
@@ -156,6 +164,11 @@ __device__ __forceinline__ Unit decode_unit(const NNParams &p, int blk) {
 }
 __device__ __forceinline__ int group_of(const Unit &u) { return u.d * 0x40000000 + u.cloud; }
 
+struct Frame {        // filter frame of one unit (identical in every helper thread)
+    float cx, cy, cz, cs, wmax;   // centre, power-of-two scale, max |t'|^2
+    int bad, bsel;                // non-finite target seen; B / raw-target buffer
+};
+
 // DBG: instrumented build -- dumps every filter value to dbg[(unit*128 + row) * dbg_ld + target] when dbg != nullptr
 // (calibration / bring-up) and writes phase clocks to prof (tools/tc_phase_clocks.py) when prof != nullptr.
 template <bool DBG>
@@ -164,16 +177,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     float *sraw = reinterpret_cast<float *>(smem + kOffRaw);
     float *part = reinterpret_cast<float *>(smem + kOffPart);
     float *sq = reinterpret_cast<float *>(smem + kOffSq);
-    int *fb_list = reinterpret_cast<int *>(smem + kOffFb);
     float *s_wstat = reinterpret_cast<float *>(smem + kOffStat);
-    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + kConsWarps;
-    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 2 * kConsWarps;
+    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + kHelpWarps;
+    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 2 * kHelpWarps;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffMisc);
-    int *s_nfb = reinterpret_cast<int *>(smem + kOffMisc) + 1;
     volatile int *s_abort = reinterpret_cast<volatile int *>(smem + kOffMisc) + 2;
     const uint32_t sB_addr = smem_u32(smem + kOffB), sA_addr = smem_u32(smem + kOffA);
     const uint32_t bar0 = smem_u32(smem + kOffBar);
-    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kBufs, bar_ready = bar0 + 16 * kBufs;
+    const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * kBufs, bar_ready = bar0 + 16 * kBufs, bar_part = bar_ready + 16;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -187,12 +198,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 
     if (tid == 0) {
         for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 4); }
-        mbar_init(bar_ready, 1);
-        *s_nfb = 0;
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_ready + 8 * i, 1); mbar_init(bar_part + 8 * i, kScanWarps); }
         *s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kConsWarps) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -202,77 +212,144 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     const uint32_t tmem_base = *s_tmem;
     if (tid == 0) stamp(1);
 
-    if (warp == kConsWarps) {
-        // ================================================= MMA warp
-        int g = 0;
+    if (warp < kScanWarps) {
+        // ================================================= scanners
+        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column group (tiles with g % 2 == c)
+        const int row = r * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(r * 32) << 16);
+        int g0 = 0;
+        long long a59 = 0;
         for (int ul = 0; ul < nunits; ++ul) {
             const Unit u = decode_unit(p, blk_begin + ul);
             const int ntiles = (p.dir[u.d].nt + kTileN - 1) / kTileN;
-            long long w0 = DBG ? clock64() : 0;
-            mbar_wait(bar_ready, ul & 1, s_abort);
-            if (DBG && pf && lane == 0) pf[56] += clock64() - w0;
-            tc_fence_after();
-            for (int t = 0; t < ntiles; ++t, ++g) {
-                const int b = g & (kBufs - 1);
-                w0 = DBG ? clock64() : 0;
-                mbar_wait(bar_empty + 8 * b, ((g >> 2) & 1) ^ 1, s_abort);
-                if (DBG && pf && lane == 0) pf[57] += clock64() - w0;
+            float best = kBig, second = kBig;
+            int bchunk = 0;
+            auto chunk = [&](const uint32_t (&v)[32], int cid) {
+                const float m = min32(v);
+                second = fminf(second, fmaxf(best, m));
+                const bool lt = m < best;
+                best = fminf(best, m);
+                bchunk = lt ? cid : bchunk;
+            };
+            for (int t = (c - g0) & 1; t < ntiles; t += 2) {
+                const int gg = g0 + t;
+                const int b = gg & (kBufs - 1);
+                const long long w0 = DBG ? clock64() : 0;
+                mbar_wait(bar_full + 8 * b, (gg >> 2) & 1, s_abort);
+                if (DBG) a59 += clock64() - w0;
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(b * kTileN);
-                    umma_f16(d_tmem, umma_desc(sA_addr), umma_desc(sB_addr + (uint32_t)t * (kTileN * 32)), 0u);
-                    umma_commit(bar_full + 8 * b);
+                const uint32_t ta = tlane + (uint32_t)(b * kTileN);
+                uint32_t ra[32], rb[32];
+                tmem_ld64_wait(ta, ra, rb);
+                if (DBG && dbg) {
+                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
                 }
+                chunk(ra, t * 4);
+                chunk(rb, t * 4 + 1);
+                tmem_ld64_wait(ta + 64, ra, rb);
+                // every column of the tile is in registers: hand the TMEM buffer back before the remaining min work
+                tc_fence_before();
                 __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                if (DBG && dbg) {
+                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                }
+                chunk(ra, t * 4 + 2);
+                chunk(rb, t * 4 + 3);
             }
-            if (DBG && pf && lane == 0) pf[58] = clock64();
+            g0 += ntiles;
+            {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
+                float *pp = part + ((ul & 1) * 2 + c) * 3 * kQB;
+                pp[row] = best; pp[kQB + row] = second; reinterpret_cast<int *>(pp)[2 * kQB + row] = bchunk;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_part + 8 * (ul & 1));
+            if (tid == 0) stamp(8 + ul * 6);
         }
+        if (DBG && pf && tid == 0) pf[59] = a59;
+    } else if (warp == kMmaWarp) {
+        // ================================================= MMA issuer: ONE thread runs the whole loop (an elected
+        // issue inside a warp-wide loop costs ~270 cycles per tile on B200, a single-thread loop 64: tools/ubench_umma.cu)
+        if (lane == 0) {
+            int g = 0, grp = -1, bsel = 1;
+            long long a56 = 0, a57 = 0, a61 = 0, a62 = 0;   // DBG: wait / issue cycle totals
+            for (int ul = 0; ul < nunits; ++ul) {
+                const Unit u = decode_unit(p, blk_begin + ul);
+                const int ntiles = (p.dir[u.d].nt + kTileN - 1) / kTileN;
+                if (group_of(u) != grp) { grp = group_of(u); bsel ^= 1; }
+                long long w0 = DBG ? clock64() : 0;
+                mbar_wait(bar_ready + 8 * (ul & 1), (ul >> 1) & 1, s_abort);
+                if (DBG) a56 += clock64() - w0;
+                tc_fence_after();
+                const uint64_t adesc = umma_desc(sA_addr + (uint32_t)(ul & 1) * (kQB * 32));
+                uint64_t bdesc = umma_desc(sB_addr + (uint32_t)bsel * (kMaxT * 32));
+                for (int t = 0; t < ntiles; ++t, ++g) {
+                    const int b = g & (kBufs - 1);
+                    w0 = DBG ? clock64() : 0;
+                    mbar_wait(bar_empty + 8 * b, ((g >> 2) & 1) ^ 1, s_abort);
+                    if (DBG) a57 += clock64() - w0;
+                    tc_fence_after();
+                    const long long w1 = DBG ? clock64() : 0;
+                    umma_f16(tmem_base + (uint32_t)(b * kTileN), adesc, bdesc, 0u);
+                    const long long w2 = DBG ? clock64() : 0;
+                    umma_commit(bar_full + 8 * b);
+                    if (DBG) { const long long w3 = clock64(); a61 += w2 - w1; a62 += w3 - w2; }
+                    bdesc += (uint64_t)((kTileN * 32) >> 4);   // next 128 targets: start-address field, 16-byte units
+                }
+            }
+            if (DBG && pf) { pf[56] = a56; pf[57] = a57; pf[58] = clock64(); pf[61] = a61; pf[62] = a62; }
+        }
+        __syncwarp();
     } else {
-        // ================================================= consumer warps
-        const int r = warp & 3, c = warp >> 2;
-        const int row = r * 32 + lane;
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(r * 32) << 16) + (uint32_t)(c * kTileN);
+        // ================================================= helpers
+        const int ht = tid - kHelp0, hw = warp - (kScanWarps + 1);
+        int st_group = -1, st_bsel = 1;      // cloud/direction of the most recently staged B operand; its buffer
+        Frame fr_st = {0.f, 0.f, 0.f, 1.f, 0.f, 0, 0};   // frame of the most recently staged unit
+        float pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;   // raw query of the unit being staged (threads < 128), loaded early
+        bool need_b = false;
 
-        // frame of the resident B operand (identical in every thread)
-        int res_group = -1, res_buf = 0;      // cloud/direction whose B operand is resident; its raw-target buffer
-        float cx = 0.f, cy = 0.f, cz = 0.f, cs = 1.f, res_wmax = 0.f;   // centre, power-of-two scale, max |t'|^2
-        int res_bad = 0;
-        int pf_group = -1, pf_buf = 1;        // cloud/direction of the most recent raw-target prefetch; its buffer
-
-        // cp.async prefetch of unit ul's raw queries (and raw targets if its cloud/direction is not the prefetched one)
-        auto prefetch = [&](int ul) {
+        // does staging unit ul replace the B operand?  (uniform)
+        auto stage_changes_group = [&](int ul) { return group_of(decode_unit(p, blk_begin + ul)) != st_group; };
+        // stage, part 1: put the global loads of unit ul in flight -- its 128 raw queries into registers and, if its
+        // cloud/direction is not the staged one, its raw targets into sraw[other buffer] by cp.async.
+        auto stage_issue = [&](int ul) {
             const Unit u = decode_unit(p, blk_begin + ul);
             const NNDirection &D = p.dir[u.d];
-            if (tid < 3 * kQB) {
-                const int comp = tid >> 7, ql = tid & (kQB - 1);
-                int j = D.q_begin + u.qblock * kQB + ql;
+            if (ht < kQB) {
+                int j = D.q_begin + u.qblock * kQB + ht;
                 const int q_last = D.q_begin + D.q_count - 1;
                 j = j < q_last ? j : q_last;
-                cp_async4(sq + ((ul % 3) * 3 + comp) * kQB + ql, D.q + (long long)u.cloud * D.q_bs + j * D.q_ps + comp * D.q_cs);
+                const float *qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
+                pq1 = __ldg(qp); pq2 = __ldg(qp + D.q_cs); pq3 = __ldg(qp + 2 * D.q_cs);
             }
             const int group = group_of(u);
-            if (group != pf_group) {
-                pf_buf ^= 1;
-                pf_group = group;
-                const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
+            need_b = group != st_group;
+            if (need_b) {
+                st_group = group;
+                st_bsel ^= 1;
                 const int nt = D.nt;
+                const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
+                const long long tps = D.t_ps, tcs = D.t_cs;
+                float *rx = sraw + (st_bsel * 3) * kMaxT;
 #pragma unroll
                 for (int comp = 0; comp < 3; ++comp)
-                    for (int k = tid; k < nt; k += kConsThreads)
-                        cp_async4(sraw + (pf_buf * 3 + comp) * kMaxT + k, tb + k * D.t_ps + comp * D.t_cs);
+                    for (int k = ht; k < nt; k += kHelpThreads) cp_async4(rx + comp * kMaxT + k, tb + k * tps + comp * tcs);
             }
         };
-        // does prefetch(ul) load raw targets?  (uniform; decided before the call to place a barrier in front of it)
-        auto prefetch_needs_targets = [&](int ul) { return group_of(decode_unit(p, blk_begin + ul)) != pf_group; };
-
-        // build the tensor-core operands of unit ul from the prefetched raw data (shared memory only)
-        auto stage = [&](int ul) {
+        // stage, part 2: build the operands of unit ul in shared memory and signal the MMA warp.
+        auto stage_finish = [&](int ul) {
             const Unit u = decode_unit(p, blk_begin + ul);
             const NNDirection &D = p.dir[u.d];
-            const int group = group_of(u);
-            if (group != res_group) {
+            if (need_b) {
                 const int nt = D.nt;
-                const float *rx = sraw + (pf_buf * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
+                const float *rx = sraw + (st_bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
+                cp_async_wait_all();
+                help_bar();   // every helper's raw targets have landed
+                float cx, cy, cz;
                 {   // centre of the filter frame: mean of up to 8 evenly spaced targets (any value is correct)
                     float sx = 0.f, sy = 0.f, sz = 0.f;
                     const int ns = nt < 8 ? nt : 8;
@@ -287,21 +364,23 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     const float inv = 1.0f / (float)ns;
                     cx = sx * inv; cy = sy * inv; cz = sz * inv;
                 }
-                // pass 1: extent of the cloud around the centre -> power-of-two scale with max|t'|_inf in [0.5, 1)
+                // pass 1: extent around the centre -> power-of-two scale
                 float cmax = 0.f;
                 int bad = 0;
-                for (int k = tid; k < nt; k += kConsThreads) {
+#pragma unroll 4
+                for (int k = ht; k < nt; k += kHelpThreads) {
                     const float ax = fabsf(rx[k] - cx), ay = fabsf(ry[k] - cy), az = fabsf(rz[k] - cz);
                     bad |= !(ax < 1e18f) | !(ay < 1e18f) | !(az < 1e18f);
                     cmax = fmaxf(cmax, fmaxf(ax, fmaxf(ay, az)));
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-                if (lane == 0) s_cstat[warp] = cmax;
-                cons_bar();
+                if (lane == 0) s_cstat[hw] = cmax;
+                help_bar();
                 cmax = 0.f;
 #pragma unroll
-                for (int w = 0; w < kConsWarps; ++w) cmax = fmaxf(cmax, s_cstat[w]);
+                for (int w = 0; w < kHelpWarps; ++w) cmax = fmaxf(cmax, s_cstat[w]);
+                float cs;
                 {
                     int e = (int)((__float_as_uint(cmax) >> 23) & 0xffu);   // biased exponent; 0 for cmax == 0 / subnormal
                     e = e < 27 ? 27 : (e > 227 ? 227 : e);                   // keep s within [2^-101, 2^99]
@@ -310,26 +389,27 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 // pass 2: scaled, split B operand
                 const int npad = ((nt + kTileN - 1) / kTileN) * kTileN;
                 float wmax = 0.f;
-                for (int k = tid; k < npad; k += kConsThreads) {
+                unsigned char *sBb = smem + kOffB + st_bsel * (kMaxT * 32);
+#pragma unroll 2
+                for (int k = ht; k < npad; k += kHelpThreads) {
                     uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
                     if (k < nt) {
                         const float x = (rx[k] - cx) * cs, y = (ry[k] - cy) * cs, z = (rz[k] - cz) * cs;
                         const float w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
                         bad |= !(w < 4.0f);
                         wmax = fmaxf(wmax, w);
-                        unsigned short xh, xl, yh, yl, zh, zl, w1, w2, w3;
+                        unsigned short xh, xl, yh, yl, zh, zl;
                         split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
                         const __half hw1 = __float2half_rn(w);
                         const float wr = w - __half2float(hw1);
                         const __half hw2 = __float2half_rn(wr);
                         const __half hw3 = __float2half_rn(wr - __half2float(hw2));
-                        w1 = __half_as_ushort(hw1); w2 = __half_as_ushort(hw2); w3 = __half_as_ushort(hw3);
                         v0 = make_uint4(pack2(xh, xl), pack2(xh, yh), pack2(yl, yh), pack2(zh, zl));
-                        v1 = make_uint4(pack2(zh, w1), pack2(w2, w3), 0u, 0u);
+                        v1 = make_uint4(pack2(zh, __half_as_ushort(hw1)), pack2(__half_as_ushort(hw2), __half_as_ushort(hw3)), 0u, 0u);
                     } else {
                         v1.x = pack2(0, __half_as_ushort(__float2half_rn(kPadW)));
                     }
-                    unsigned char *dst = smem + kOffB + (k >> 3) * 256 + (k & 7) * 16;
+                    unsigned char *dst = sBb + (k >> 3) * 256 + (k & 7) * 16;
                     *reinterpret_cast<uint4 *>(dst) = v0;
                     *reinterpret_cast<uint4 *>(dst + 128) = v1;
                 }
@@ -338,65 +418,147 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
                     bad |= __shfl_xor_sync(0xffffffffu, bad, o);
                 }
-                if (lane == 0) { s_wstat[warp] = wmax; s_bstat[warp] = bad; }
+                if (lane == 0) { s_wstat[hw] = wmax; s_bstat[hw] = bad; }
+                fr_st.cx = cx; fr_st.cy = cy; fr_st.cz = cz; fr_st.cs = cs; fr_st.bsel = st_bsel;
+                fr_st.wmax = -1.f;   // statistics are picked up after the barrier below
             }
-            if (tid < kQB) {
-                const float *sqp = sq + (ul % 3) * 3 * kQB;
-                const float sc = -2.0f * cs;
-                const float x = (sqp[tid] - cx) * sc, y = (sqp[kQB + tid] - cy) * sc, z = (sqp[2 * kQB + tid] - cz) * sc;
+            if (ht < kQB) {
+                float *sqp = sq + (ul % 3) * 3 * kQB;
+                sqp[ht] = pq1; sqp[kQB + ht] = pq2; sqp[2 * kQB + ht] = pq3;
+                const float sc = -2.0f * fr_st.cs;
+                const float x = (pq1 - fr_st.cx) * sc, y = (pq2 - fr_st.cy) * sc, z = (pq3 - fr_st.cz) * sc;
                 unsigned short xh, xl, yh, yl, zh, zl;
                 split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
                 const unsigned short one = 0x3c00;
-                unsigned char *dst = smem + kOffA + (tid >> 3) * 256 + (tid & 7) * 16;
+                unsigned char *dst = smem + kOffA + (ul & 1) * (kQB * 32) + (ht >> 3) * 256 + (ht & 7) * 16;
                 *reinterpret_cast<uint4 *>(dst) = make_uint4(pack2(xh, xh), pack2(xl, yh), pack2(yh, yl), pack2(zh, zh));
                 *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(pack2(zl, one), pack2(one, one), 0u, 0u);
             }
             fence_async_smem();
-            return group;
-        };
-        // after the barrier that follows stage(): pick up the statistics of a freshly staged B operand
-        auto adopt = [&](int group) {
-            if (group != res_group) {
+            help_bar();
+            if (ht == 0) mbar_arrive(bar_ready + 8 * (ul & 1));
+            if (fr_st.wmax < 0.f) {
                 float wmax = 0.f;
                 int bad = 0;
 #pragma unroll
-                for (int w = 0; w < kConsWarps; ++w) { wmax = fmaxf(wmax, s_wstat[w]); bad |= s_bstat[w]; }
-                res_wmax = wmax; res_bad = bad; res_group = group; res_buf = pf_buf;
+                for (int w = 0; w < kHelpWarps; ++w) { wmax = fmaxf(wmax, s_wstat[w]); bad |= s_bstat[w]; }
+                fr_st.wmax = wmax; fr_st.bad = bad;
             }
         };
 
-        // exact full scan for the queries on the deferred list, one warp per query.  Reference semantics incl. NaN:
-        // within a 512-target tile the first element is taken unconditionally and NaN never replaces or is replaced
-        // (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
-        auto run_fallbacks = [&](int nfb) {
-            for (int fi = warp; fi < nfb; fi += kConsWarps) {
-                const int e = fb_list[fi];
-                const bool ebad = (e >> 30) & 1;
-                const Unit u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
-                const NNDirection &D = p.dir[u.d];
-                const int nt = D.nt;
-                const int j = D.q_begin + u.qblock * kQB + (e & 0xff);
-                const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
-                const float *__restrict__ qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
-                const long long tps = D.t_ps, tcs = D.t_cs;
-                const float x1 = __ldg(qp), y1 = __ldg(qp + D.q_cs), z1 = __ldg(qp + 2 * D.q_cs);
-                const bool nan_possible = ebad || !(fabsf(x1) < 1e18f) || !(fabsf(y1) < 1e18f) || !(fabsf(z1) < 1e18f);
-                unsigned long long key = ~0ull;
-                for (int kb = lane; kb < nt; kb += 8 * 32) {
-                    float dd[8], dts[8];
+        // resolve unit ul.  Warp hw owns the queries [hw*kQW, hw*kQW + kQW) of the unit:
+        //   A  lane = query: merge the two scanner partials, margin test
+        //   B  4 lanes per query: exact rescan of the best chunk (32 targets) from the raw targets in shared memory
+        //   C  whole warp per query: exact full scan for the queries that failed the margin test.  Reference semantics
+        //      incl. NaN: within a 512-target tile the first element is taken unconditionally and NaN never replaces or
+        //      is replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+        constexpr int kQW = (kQB + kHelpWarps - 1) / kHelpWarps;   // 19
+        auto resolve = [&](int ul, const Frame &fr) {
+            const Unit u = decode_unit(p, blk_begin + ul);
+            const NNDirection &D = p.dir[u.d];
+            const int nt = D.nt;
+            const float *pp = part + (ul & 1) * 2 * 3 * kQB;
+            const float *sqp = sq + (ul % 3) * 3 * kQB;
+            const float *rx = sraw + (fr.bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
+            const int q0 = hw * kQW;
+            const int nqw = min(kQW, kQB - q0);
+            // ---- A
+            const int ql = q0 + (lane < nqw ? lane : 0);
+            const int j = D.q_begin + u.qblock * kQB + ql;
+            const bool live = lane < nqw && j < D.q_begin + D.q_count;
+            float b1 = kBig, b2 = kBig;
+            int bc = 0;
 #pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8) {
-                        const int k = min(kb + q8 * 32, nt - 1);
-                        dd[q8] = exact_d(tb, tps, tcs, k, x1, y1, z1);
-                        dts[q8] = nan_possible ? exact_d(tb, tps, tcs, k & ~(kRefTile - 1), x1, y1, z1) : 0.f;
+            for (int w = 0; w < 2; ++w) {
+                const float v = pp[w * 3 * kQB + ql];
+                b2 = fminf(b2, fminf(pp[w * 3 * kQB + kQB + ql], fmaxf(b1, v)));
+                if (v < b1) { b1 = v; bc = reinterpret_cast<const int *>(pp)[w * 3 * kQB + 2 * kQB + ql]; }
+            }
+            const float x1 = sqp[ql], y1 = sqp[kQB + ql], z1 = sqp[2 * kQB + ql];
+            const float ux = (x1 - fr.cx) * fr.cs, uy = (y1 - fr.cy) * fr.cs, uz = (z1 - fr.cz) * fr.cs;   // scaled frame
+            const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
+            // Filter error bound E = 25u*S (u = 2^-24): frame 2u, |t'|^2 3u, operand splits 12u, tensor-core accumulation
+            // 8u (measured total on B200: <= 4.1u, tools/tc_calibrate.py).  The reference's argmin lies in the best chunk
+            // if second > best + 2E + 10u*S.
+            //   S  = (|q'| + max|t'|)^2 bounds every target,
+            //   S' = (2|q'| + rho)^2 bounds the targets that can compete (within rho of the query).
+            const float qn = sqrtf(qq);
+            const float rr = qn + sqrtf(fr.wmax);
+            const float S = rr * rr;
+            const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 2.4e-6f * S);
+            const float r2 = 2.0f * qn + rho;
+            const float Seff = fminf(S, r2 * r2);
+            const float margin = __fmaf_rn(Seff, 3.7e-6f, 1e-36f);
+            const bool ok = live && !fr.bad && (qn < kQMax) && (b2 > b1 + margin);
+            float ws = 0.f;   // fused epilogue accumulators of this lane
+            int wc = 0;
+            // ---- B
+#pragma unroll
+            for (int it = 0; it < (kQW * 4 + 31) / 32; ++it) {
+                const int lt = it * 32 + lane;
+                const int qi = lt >> 2, sub = lt & 3;          // qi < 24: a valid source lane
+                const bool okq = __shfl_sync(0xffffffffu, (int)ok, qi) != 0;
+                const int bcq = __shfl_sync(0xffffffffu, bc, qi);
+                const float xq = __shfl_sync(0xffffffffu, x1, qi), yq = __shfl_sync(0xffffffffu, y1, qi),
+                            zq = __shfl_sync(0xffffffffu, z1, qi);
+                const int jq = __shfl_sync(0xffffffffu, j, qi);
+                int k0 = bcq * kCh + sub * 8;
+                const bool act = okq && k0 < nt;
+                k0 = act ? k0 : 0;
+                const float4 xa = *reinterpret_cast<const float4 *>(rx + k0), xb = *reinterpret_cast<const float4 *>(rx + k0 + 4);
+                const float4 ya = *reinterpret_cast<const float4 *>(ry + k0), yb = *reinterpret_cast<const float4 *>(ry + k0 + 4);
+                const float4 za = *reinterpret_cast<const float4 *>(rz + k0), zb = *reinterpret_cast<const float4 *>(rz + k0 + 4);
+                const float tx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                const float ty[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                const float tz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                float dbest = 3.0e38f;
+                int ibest = 0x7fffffff;
+                if (act) {
+                    dbest = sqdist_exact(tx[0] - xq, ty[0] - yq, tz[0] - zq);
+                    ibest = k0;
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) {
+                        const float dv = sqdist_exact(tx[i] - xq, ty[i] - yq, tz[i] - zq);
+                        if (k0 + i < nt && dv < dbest) { dbest = dv; ibest = k0 + i; }
                     }
+                }
+                // quad merge: smaller distance wins, equal distances -> lower index (sub-ranges are index-ordered)
 #pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8) {
-                        const int k = kb + q8 * 32;
-                        if (k < nt && !(dd[q8] != dd[q8]) && !(dts[q8] != dts[q8])) {
-                            const unsigned long long kk = pack_key(dd[q8], k);
-                            key = kk < key ? kk : key;
-                        }
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, dbest, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, ibest, o);
+                    if (od < dbest || (od == dbest && oi < ibest)) { dbest = od; ibest = oi; }
+                }
+                if (okq && sub == 0) {
+                    D.dist[(long long)u.cloud * D.nq + jq] = dbest;
+                    D.idx[(long long)u.cloud * D.nq + jq] = ibest;
+                    ws += dbest;
+                    wc += dbest < p.fs_thr ? 1 : 0;
+                }
+            }
+            // ---- C
+            unsigned fbm = __ballot_sync(0xffffffffu, live && !ok);
+            if (fbm != 0u && lane == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)__popc(fbm));
+            while (fbm != 0u) {
+                const int qi = __ffs(fbm) - 1;
+                fbm &= fbm - 1u;
+                const float xq = __shfl_sync(0xffffffffu, x1, qi), yq = __shfl_sync(0xffffffffu, y1, qi),
+                            zq = __shfl_sync(0xffffffffu, z1, qi);
+                const int jq = __shfl_sync(0xffffffffu, j, qi);
+                const bool nan_possible = fr.bad || !(fabsf(xq) < 1e18f) || !(fabsf(yq) < 1e18f) || !(fabsf(zq) < 1e18f);
+                unsigned long long key = ~0ull;
+#pragma unroll 4
+                for (int k = lane; k < nt; k += 32) {
+                    const float dd = sqdist_exact(rx[k] - xq, ry[k] - yq, rz[k] - zq);
+                    bool good = !(dd != dd);
+                    if (nan_possible) {
+                        const int kt = k & ~(kRefTile - 1);
+                        const float dts = sqdist_exact(rx[kt] - xq, ry[kt] - yq, rz[kt] - zq);
+                        good = good && !(dts != dts);
+                    }
+                    if (good) {
+                        const unsigned long long kk = pack_key(dd, k);
+                        key = kk < key ? kk : key;
                     }
                 }
 #pragma unroll
@@ -405,214 +567,63 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     key = other < key ? other : key;
                 }
                 if (lane == 0) {
-                    const float d0 = exact_d(tb, tps, tcs, 0, x1, y1, z1);
+                    const float d0 = sqdist_exact(rx[0] - xq, ry[0] - yq, rz[0] - zq);
                     float dres;
                     int ires;
                     if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
                     else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
-                    D.dist[(long long)u.cloud * D.nq + j] = dres;
-                    D.idx[(long long)u.cloud * D.nq + j] = ires;
-                    if (p.sums) atomicAdd(p.sums + u.cloud * 2 + D.slot, dres);
-                    if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + u.cloud * 2 + D.slot, 1);
+                    D.dist[(long long)u.cloud * D.nq + jq] = dres;
+                    D.idx[(long long)u.cloud * D.nq + jq] = ires;
+                    ws += dres;
+                    wc += dres < p.fs_thr ? 1 : 0;
                 }
             }
-            if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
+            if (p.sums != nullptr || p.fs_count != nullptr) {   // fused epilogues, one atomic per warp
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ws += __shfl_xor_sync(0xffffffffu, ws, o);
+                    wc += __shfl_xor_sync(0xffffffffu, wc, o);
+                }
+                if (lane == 0) {
+                    if (p.sums) atomicAdd(p.sums + u.cloud * 2 + D.slot, ws);
+                    if (p.fs_count && wc) atomicAdd(p.fs_count + u.cloud * 2 + D.slot, wc);
+                }
+            }
         };
 
-        if (nunits > 0) {
-            prefetch(0);
-            cp_async_wait_all();
-            cons_bar();
-            const int grp = stage(0);
-            cons_bar();
-            adopt(grp);
-            if (tid == 0) mbar_arrive(bar_ready);
-        }
-        if (tid == 0) stamp(2);
-        int g0 = 0;
+        Frame f0 = fr_st, f1 = fr_st;     // frames of unit ul and ul + 1
+        if (nunits > 0) { stage_issue(0); stage_finish(0); f0 = fr_st; }
+        if (nunits > 1) { stage_issue(1); stage_finish(1); f1 = fr_st; }
+        if (ht == 0) stamp(2);
+        long long a60 = 0;
         for (int ul = 0; ul < nunits; ++ul) {
-            const Unit u = decode_unit(p, blk_begin + ul);
-            const NNDirection &D = p.dir[u.d];
-            const int nt = D.nt;
-            const int ntiles = (nt + kTileN - 1) / kTileN;
-            // ---------------- raw data of the next unit: in flight during the scan
-            if (ul + 1 < nunits) {
-                // a target prefetch reuses the raw buffer of the previous cloud/direction, which slower warps may still
-                // be reading in the resolve phase of the previous unit
-                if (prefetch_needs_targets(ul + 1)) cons_bar();
-                prefetch(ul + 1);
+            // Loads of unit ul+2 go in flight before the resolve work.  Its raw targets may only be prefetched here when
+            // their buffer is not the one resolve(ul) still reads: units ul and ul+1 of the same cloud/direction.
+            const bool stage_next = ul + 2 < nunits;
+            bool issued = false;
+            if (stage_next && (!stage_changes_group(ul + 2) || f0.bsel == f1.bsel)) { stage_issue(ul + 2); issued = true; }
+            const long long w0 = DBG ? clock64() : 0;
+            mbar_wait(bar_part + 8 * (ul & 1), (ul >> 1) & 1, s_abort);   // scanners parked unit ul; its MMAs are complete
+            if (DBG) a60 += clock64() - w0;
+            if (ht == 0) stamp(9 + ul * 6);
+            resolve(ul, f0);
+            if (ht == 0) stamp(10 + ul * 6);
+            help_bar();   // every helper is done with part/sq/sraw of unit ul before anything is restaged
+            f0 = f1;
+            if (stage_next) {
+                if (!issued) stage_issue(ul + 2);
+                stage_finish(ul + 2);
+                f1 = fr_st;
             }
-            // ---------------- scan: tiles whose TMEM buffer is this warp's column group; 16-column loads, one in flight
-            float best = kBig, second = kBig;
-            int bchunk = 0;
-            for (int t = (c - g0) & (kBufs - 1); t < ntiles; t += kBufs) {
-                const int gg = g0 + t;
-                const long long w0 = DBG ? clock64() : 0;
-                mbar_wait(bar_full + 8 * c, (gg >> 2) & 1, s_abort);
-                if (DBG && pf && tid == 0) pf[59] += clock64() - w0;
-                tc_fence_after();
-                uint32_t ra[16], rb[16];
-                tmem_ld16(taddr0, ra);
-                float mprev = 0.f;
-#pragma unroll
-                for (int h = 0; h < kTileN / 16; ++h) {
-                    float mh;
-                    if ((h & 1) == 0) {
-                        tmem_wait(ra);
-                        tmem_ld16(taddr0 + (uint32_t)((h + 1) * 16), rb);
-                        if (DBG && dbg) {
-                            float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + h * 16;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(ra[i]);
-                        }
-                        mh = min16(ra);
-                        mprev = mh;
-                    } else {
-                        tmem_wait(rb);
-                        if (h + 1 < kTileN / 16) tmem_ld16(taddr0 + (uint32_t)((h + 1) * 16), ra);
-                        if (DBG && dbg) {
-                            float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + h * 16;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(rb[i]);
-                        }
-                        mh = min16(rb);
-                        const float v = fminf(mprev, mh);
-                        second = fminf(second, fmaxf(best, v));
-                        const bool lt = v < best;
-                        best = fminf(best, v);
-                        bchunk = lt ? t * (kTileN / kCh) + (h >> 1) : bchunk;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * c);
-            }
-            g0 += ntiles;
-            if (tid == 0) stamp(8 + ul * 6);
-            {   // park this warp's partial results (double-buffered by unit parity)
-                float *pp = part + ((ul & 1) * 4 + c) * 3 * kQB;
-                pp[row] = best; pp[kQB + row] = second; reinterpret_cast<int *>(pp)[2 * kQB + row] = bchunk;
-            }
-            // frame of THIS unit, before staging possibly replaces it
-            const float ucx = cx, ucy = cy, ucz = cz, ucs = cs, u_wmax = res_wmax;
-            const int u_bad = res_bad, u_buf = res_buf;
-            cp_async_wait_all();
-            cons_bar();   // S1: all tiles of the unit consumed (every MMA that reads A/B has completed), partials parked,
-                          //     prefetched raw data of the next unit visible
-            if (tid == 0) stamp(9 + ul * 6);
-            {   // deferred exact scans: flush when the next unit could overflow the list
-                const int nfb = *s_nfb;
-                if (nfb > kFbCap - kQB) {
-                    run_fallbacks(nfb);
-                    cons_bar();
-                    if (tid == 0) *s_nfb = 0;
-                }
-            }
-            int grp = res_group;
-            if (ul + 1 < nunits) grp = stage(ul + 1);
-            cons_bar();   // S2: operands of the next unit are in shared memory (also orders the list reset above)
-            if (ul + 1 < nunits) {
-                adopt(grp);
-                if (tid == 0) mbar_arrive(bar_ready);
-            }
-            if (tid == 0) stamp(10 + ul * 6);
-
-            // ---------------- resolve: 4 threads per query, raw targets from shared memory
-            {
-                const int ql = tid >> 2, sub = tid & 3;
-                const int j = D.q_begin + u.qblock * kQB + ql;
-                const bool live = j < D.q_begin + D.q_count;
-                const float *pp = part + (ul & 1) * 4 * 3 * kQB;
-                float b1 = kBig, b2 = kBig;
-                int bc = 0;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const float v = pp[w * 3 * kQB + ql];
-                    b2 = fminf(b2, fminf(pp[w * 3 * kQB + kQB + ql], fmaxf(b1, v)));
-                    if (v < b1) { b1 = v; bc = reinterpret_cast<const int *>(pp)[w * 3 * kQB + 2 * kQB + ql]; }
-                }
-                const float *sqp = sq + (ul % 3) * 3 * kQB;
-                const float x1 = sqp[ql], y1 = sqp[kQB + ql], z1 = sqp[2 * kQB + ql];
-                const float ux = (x1 - ucx) * ucs, uy = (y1 - ucy) * ucs, uz = (z1 - ucz) * ucs;   // scaled frame, like the filter
-                const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
-                // Filter error bound E = 25u*S (u = 2^-24): frame 2u, |t-c|^2 3u, operand splits 12u, tensor-core
-                // accumulation 8u (measured total on B200: <= 4.1u, tools/tc_calibrate.py).  The reference's argmin
-                // lies in the best chunk if second > best + 2E + 10u*S.
-                //   S  = (|q-c| + max|t-c|)^2 bounds every target,
-                //   S' = (2|q-c| + rho)^2 bounds the targets that can compete (within rho of the query).
-                const float qn = sqrtf(qq);
-                const float rr = qn + sqrtf(u_wmax);
-                const float S = rr * rr;
-                const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 2.4e-6f * S);
-                const float r2 = 2.0f * qn + rho;
-                const float Seff = fminf(S, r2 * r2);
-                const float margin = __fmaf_rn(Seff, 3.7e-6f, 1e-36f);
-                const bool ok = live && !u_bad && (qn < kQMax) && (b2 > b1 + margin);
-                float dres = 0.f;
-                bool done = false;
-                if (ok) {
-                    const int k0 = bc * kCh + sub * 8;
-                    float dbest = 3.0e38f;
-                    int ibest = 0x7fffffff;
-                    if (k0 < nt) {
-                        const float4 *px = reinterpret_cast<const float4 *>(sraw + (u_buf * 3) * kMaxT + k0);
-                        const float4 *py = reinterpret_cast<const float4 *>(sraw + (u_buf * 3 + 1) * kMaxT + k0);
-                        const float4 *pz = reinterpret_cast<const float4 *>(sraw + (u_buf * 3 + 2) * kMaxT + k0);
-                        const float4 xa = px[0], xb = px[1], ya = py[0], yb = py[1], za = pz[0], zb = pz[1];
-                        const float tx[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-                        const float ty[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-                        const float tz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-                        dbest = sqdist_exact(tx[0] - x1, ty[0] - y1, tz[0] - z1);
-                        ibest = k0;
-#pragma unroll
-                        for (int i = 1; i < 8; ++i) {
-                            const float dv = sqdist_exact(tx[i] - x1, ty[i] - y1, tz[i] - z1);
-                            if (k0 + i < nt && dv < dbest) { dbest = dv; ibest = k0 + i; }
-                        }
-                    }
-                    // quad merge: smaller distance wins, equal distances -> lower index (sub-ranges are index-ordered)
-                    const unsigned qmask = 0xFu << (lane & ~3);
-#pragma unroll
-                    for (int o = 1; o <= 2; o <<= 1) {
-                        const float od = __shfl_xor_sync(qmask, dbest, o);
-                        const int oi = __shfl_xor_sync(qmask, ibest, o);
-                        if (od < dbest || (od == dbest && oi < ibest)) { dbest = od; ibest = oi; }
-                    }
-                    if (sub == 0) {
-                        D.dist[(long long)u.cloud * D.nq + j] = dbest;
-                        D.idx[(long long)u.cloud * D.nq + j] = ibest;
-                        dres = dbest;
-                        done = true;
-                    }
-                } else if (live && sub == 0) {
-                    fb_list[atomicAdd(s_nfb, 1)] = (ul << 8) | ql | (u_bad ? (1 << 30) : 0);
-                }
-                if (p.sums != nullptr || p.fs_count != nullptr) {   // fused epilogues, one atomic per warp
-                    float ws = done ? dres : 0.f;
-                    int wc = (done && dres < p.fs_thr) ? 1 : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        ws += __shfl_xor_sync(0xffffffffu, ws, o);
-                        wc += __shfl_xor_sync(0xffffffffu, wc, o);
-                    }
-                    if (lane == 0) {
-                        if (p.sums) atomicAdd(p.sums + u.cloud * 2 + D.slot, ws);
-                        if (p.fs_count && wc) atomicAdd(p.fs_count + u.cloud * 2 + D.slot, wc);
-                    }
-                }
-            }
-            if (tid == 0) stamp(11 + ul * 6);
+            if (ht == 0) stamp(11 + ul * 6);
         }
-        // ---------------- the deferred exact scans of this CTA
-        cons_bar();
-        if (tid == 0) stamp(3);
-        run_fallbacks(*s_nfb);
-        if (tid == 0) stamp(4);
+        if (DBG && pf && ht == 0) pf[60] = a60;
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == kConsWarps)
+    if (tid == 0) { stamp(3); stamp(4); }
+    if (warp == kMmaWarp)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 

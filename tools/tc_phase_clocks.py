@@ -38,27 +38,24 @@ P = P[act]
 print(f"B={b} N={n} M={m}: {act.sum()} CTAs")
 t0 = P[:, 0]
 print(f"  setup (barrier init, TMEM alloc)        {np.mean(P[:, 1] - t0):9.0f}")
-print(f"  stage unit 0 (B + A operands)           {np.mean(P[:, 2] - P[:, 1]):9.0f}")
-prev = P[:, 2]
-names = ["scan end", "S1 (all consumed)", "S2 (next staged)", "resolve end"]
+print(f"  helpers: units 0 and 1 staged at        {np.mean(P[:, 2] - t0):9.0f}")
+prev_scan = P[:, 2].copy()
 for u in range(8):
     base = 8 + u * 6
     have = P[:, base] > 0
     if not have.any():
         break
-    line = f"  unit {u} ({have.sum():3d} CTAs):"
-    last = prev[have]
-    for i, nm in enumerate(names):
-        cur = P[have, base + i]
-        line += f"  {nm} +{np.mean(cur - last):7.0f}"
-        last = cur
-    print(line)
-    prev = P[:, base + 3].copy()
-    prev[~have] = P[~have, 2]
-end = np.maximum(P[:, 8:56].max(axis=1), P[:, 4])
+    sc, pw, rs, st = P[have, base], P[have, base + 1], P[have, base + 2], P[have, base + 3]
+    print(f"  unit {u} ({have.sum():3d} CTAs): scanners done at {np.mean(sc - t0[have]):8.0f} (+{np.mean(sc - prev_scan[have]):6.0f})   "
+          f"helpers: partials seen {np.mean(pw - t0[have]):8.0f}, resolve +{np.mean(rs - pw):6.0f}, next staged +{np.mean(st - rs):6.0f}")
+    prev_scan[have] = sc
+print(f"  all roles done (before deferred scans)  {np.mean(P[:, 3] - t0):9.0f}")
 print(f"  deferred exact scans                    {np.mean(P[:, 4] - P[:, 3]):9.0f}")
-print(f"  consumer thread 0 total                 {np.mean(end - t0):9.0f}  (max {np.max(end - t0):.0f})")
-print(f"  consumer warp 0 waiting on full barriers{np.mean(P[:, 59]):9.0f}")
+print(f"  total                                   {np.mean(P[:, 4] - t0):9.0f}  (max {np.max(P[:, 4] - t0):.0f})")
+print(f"  scanner warp 0 waiting on full barriers {np.mean(P[:, 59]):9.0f}")
+print(f"  helpers waiting for parked partials     {np.mean(P[:, 60]):9.0f}")
 print(f"  MMA warp: waiting for operands          {np.mean(P[:, 56]):9.0f}")
 print(f"  MMA warp: waiting for empty buffers     {np.mean(P[:, 57]):9.0f}")
 print(f"  MMA warp: last issue at                 {np.mean(P[:, 58] - t0):9.0f}")
+print(f"  MMA warp: inside tcgen05.mma issue      {np.mean(P[:, 61]):9.0f}")
+print(f"  MMA warp: inside tcgen05.commit issue   {np.mean(P[:, 62]):9.0f}")

@@ -82,6 +82,122 @@ __global__ void __launch_bounds__(128, 1) umma_rate(Cfg c, int iters, long long 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+
+// Protocol cost per tile: mode 0 = MMA only; 1 = MMA + commit (round-robin over 4 mbarriers, nobody waits);
+// 2 = MMA + commit + wait for that commit (full round trip); 3 = mode 1 + tcgen05.fence::after_thread_sync per tile.
+__global__ void __launch_bounds__(128, 1) umma_protocol(int mode, int iters, long long *cycles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[4];
+    __shared__ uint32_t tmem_s;
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[i])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_s;
+    if (warp == 0) {
+        Cfg c = {0, 128, 256, 0, 4096, 128, 1, 1};
+        const uint32_t a_base = smem_u32(smem), b_base = a_base + 32 * 1024;
+        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // f16
+        const uint64_t ad = make_desc(a_base, c), bd = make_desc(b_base, c);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t d = tmem + (i & 3) * 128;
+            const uint32_t bar = smem_u32(&bars[i & 3]);
+            if (mode == 3) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d), "l"(ad), "l"(bd + (uint64_t)((i & 7) * 256)), "r"(idesc), "r"(0u) : "memory");
+                if (mode >= 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            }
+            __syncwarp();
+            if (mode == 2) {
+                uint32_t ok = 0;
+                const uint32_t parity = (i >> 2) & 1;
+                while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            }
+        }
+        // drain: one more commit and wait for it
+        if (lane == 0) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[iters & 3])) : "memory");
+        __syncwarp();
+        if (mode != 2) {
+            // wait until the final commit has flipped its barrier's phase: count the phases it has been through
+            uint32_t ok = 0;
+            const int nth = (iters + 3 - (iters & 3)) / 4 + ((mode >= 1) ? 0 : 0);
+            const uint32_t parity = (mode >= 1) ? (uint32_t)(((iters >> 2)) & 1) : 0u;
+            long long spins = 0;
+            while (!ok && spins < 50000000LL) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(&bars[iters & 3])), "r"(parity) : "memory");
+                ++spins;
+            }
+            (void)nth;
+        }
+        const long long t1 = clock64();
+        if (lane == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+
+// Which property of the per-tile pattern is slow?  One thread issues `iters` kind::f16 M128 N128 K16 MMAs:
+//   rot  : 1 = rotate over the 4 TMEM buffers, 0 = always buffer 0      acc: accumulate flag      nb: B tiles in rotation
+__global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb, int iters, long long *cycles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_s;
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_s;
+    if (warp == 0) {
+        Cfg c = {0, 128, 256, 0, 4096, 128, 1, 1};
+        const uint32_t a_base = smem_u32(smem), b_base = a_base + 32 * 1024;
+        const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // f16
+        const uint64_t ad = make_desc(a_base, c), bd = make_desc(b_base, c);
+        const long long t0 = clock64();
+        if (lane == 0) {
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t d = tmem + (rot ? (i & 3) * 128 : 0);
+                asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d), "l"(ad), "l"(bd + (uint64_t)((i & (nb - 1)) * 256)), "r"(idesc), "r"((uint32_t)acc) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        uint32_t ok = 0;
+        long long spins = 0;
+        while (!ok && spins < 100000000LL) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+            ++spins;
+        }
+        const long long t1 = clock64();
+        if (lane == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 int main() {
     long long *d_cyc, h_cyc[148];
     CK(cudaMalloc(&d_cyc, sizeof(h_cyc)));
@@ -120,5 +236,33 @@ int main() {
                bad ? "  [TIMEOUT]" : "");
         fflush(stdout);
     }
+    CK(cudaFuncSetAttribute(umma_protocol, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const char *mnames[] = {"MMA only (f16 N=128)", "MMA + commit per tile", "MMA + commit + wait per tile (round trip)", "MMA + commit + fence::after per tile"};
+    for (int mode = 0; mode < 4; ++mode) {
+        const int it = 2000;   // multiple of 4: the drain commit lands on barrier 0
+        for (int rep = 0; rep < 2; ++rep) {
+            umma_protocol<<<148, 128, 200 * 1024>>>(mode, it, d_cyc);
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h_cyc, d_cyc, sizeof(h_cyc), cudaMemcpyDeviceToHost));
+        double mean = 0;
+        for (int i = 0; i < 148; ++i) mean += h_cyc[i];
+        printf("protocol: %-45s %8.1f cycles per tile\n", mnames[mode], mean / 148 / it);
+        fflush(stdout);
+    }
+    CK(cudaFuncSetAttribute(umma_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int rot = 0; rot < 2; ++rot)
+        for (int acc = 0; acc < 2; ++acc)
+            for (int nb = 1; nb <= 16; nb *= 16) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    umma_pattern<<<148, 128, 200 * 1024>>>(rot, acc, nb, 2000, d_cyc);
+                    CK(cudaDeviceSynchronize());
+                }
+                CK(cudaMemcpy(h_cyc, d_cyc, sizeof(h_cyc), cudaMemcpyDeviceToHost));
+                double mean = 0;
+                for (int i = 0; i < 148; ++i) mean += h_cyc[i];
+                printf("pattern: rotate D=%d accumulate=%d B tiles=%2d  %8.1f cycles per MMA\n", rot, acc, nb, mean / 148 / 2000);
+                fflush(stdout);
+            }
     return 0;
 }

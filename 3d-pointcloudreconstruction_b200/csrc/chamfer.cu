@@ -583,7 +583,9 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
     p.tile = 0; p.flush = 0;
     // Tensor-core filter (chamfer_nn_tc.cu) whenever both target clouds fit its resident B operand.
-    if (g_nn_variant == 3 && psd_nn_tc_supported(p)) {   // not yet the automatic choice: v1 is slower than the FFMA kernel
+    // Measured (tools/nn_variants.py): 41.5 vs 55.8 us at B=32 N=M=2048, 70.5 vs 105.8 us at B=64, 20.3 vs 22.5 us at
+    // B=32 N=M=1024; launches of < 2 units per SM are latency-bound and stay on the FFMA kernel (8.9 vs 7.5 us at B=8 N=512).
+    if ((g_nn_variant == 3 || (g_nn_variant == 0 && blocks >= 2LL * g_num_sms)) && psd_nn_tc_supported(p)) {
         float *dbg = g_tc_dbg;
         g_tc_dbg = nullptr;
         return psd_launch_nn_tc(p, g_num_sms, stream, dbg, g_tc_dbg_ld, g_tc_prof);

@@ -25,7 +25,8 @@
 //                 matrices, double-buffered A and B), and resolve the unit the scanners just finished: merge the
 //                 partial results, margin test, exact rescan of the best chunk from raw targets kept in shared
 //                 memory, fused loss-sum / F-score epilogue.  Queries that fail the margin test go to a per-CTA
-//                 list and take an exact full scan, one warp per query, by all warps at the end.
+//                 list and take an exact full scan, one warp per query, by all warps at the end (raw targets from
+//                 shared memory when their cloud is still resident).
 // A unit is a block of 128 queries of one cloud/direction; a CTA owns a contiguous range of units.
 #include <cuda_fp16.h>
 #include "chamfer_nn.cuh"
@@ -54,8 +55,8 @@ constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][2 column groups
 constexpr int kOffSq = kOffPart + 2 * 2 * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
 constexpr int kFbCap = 512;                               // deferred exact-scan list (entries: unit << 8 | query)
 constexpr int kOffFb = kOffSq + 3 * 3 * kQB * 4;
-constexpr int kOffStat = kOffFb + kFbCap * 4;             // [8] wmax, [8] bad, [8] cmax
-constexpr int kOffBar = kOffStat + 3 * 8 * 4;             // 12 mbarriers (8-byte aligned)
+constexpr int kOffStat = kOffFb + kFbCap * 4;             // [16] wmax, [16] bad, [16] cmax, [2] group resident in sraw[i]
+constexpr int kOffBar = kOffStat + 3 * 16 * 4 + 16;       // 12 mbarriers (8-byte aligned)
 constexpr int kOffMisc = kOffBar + 16 * 8;                // tmem base, nfb, abort
 constexpr int kSmemTC = kOffMisc + 64;
 static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8, "shared-memory carve-up alignment");
@@ -169,6 +170,67 @@ struct Frame {        // filter frame of one unit (identical in every helper thr
     int bad, bsel;                // non-finite target seen; B / raw-target buffer
 };
 
+// Exact full scan for the queries on the deferred list, one warp per query; raw targets come from shared memory when
+// the query's cloud/direction is still resident in sraw, else from global memory.  Reference semantics incl. NaN:
+// within a 512-target tile the first element is taken unconditionally and NaN never replaces or is replaced
+// (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+__device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, const int *fb_list, int nfb, int wi, int nw,
+                                              int lane, const float *sraw, const int *s_rawgroup) {
+    for (int fi = wi; fi < nfb; fi += nw) {
+        const int e = fb_list[fi];
+        const bool ebad = (e >> 30) & 1;
+        const Unit u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
+        const NNDirection &D = p.dir[u.d];
+        const int nt = D.nt;
+        const int j = D.q_begin + u.qblock * kQB + (e & 0xff);
+        const float *__restrict__ qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
+        const float x1 = __ldg(qp), y1 = __ldg(qp + D.q_cs), z1 = __ldg(qp + 2 * D.q_cs);
+        const bool nan_possible = ebad || !(fabsf(x1) < 1e18f) || !(fabsf(y1) < 1e18f) || !(fabsf(z1) < 1e18f);
+        const int grp = group_of(u);
+        const int res = s_rawgroup[0] == grp ? 0 : (s_rawgroup[1] == grp ? 1 : -1);
+        // generic view of the targets: component base pointers and point stride
+        const float *bx, *by, *bz;
+        long long ps;
+        if (res >= 0) { bx = sraw + (res * 3) * kMaxT; by = bx + kMaxT; bz = by + kMaxT; ps = 1; }
+        else { bx = D.t + (long long)u.cloud * D.t_bs; by = bx + D.t_cs; bz = by + D.t_cs; ps = D.t_ps; }
+        unsigned long long key = ~0ull;
+        for (int kb = lane; kb < nt; kb += 8 * 32) {
+            float dd[8], dts[8];
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+                const long long k = min(kb + q8 * 32, nt - 1);
+                dd[q8] = sqdist_exact(bx[k * ps] - x1, by[k * ps] - y1, bz[k * ps] - z1);
+                const long long kt = k & ~(long long)(kRefTile - 1);
+                dts[q8] = nan_possible ? sqdist_exact(bx[kt * ps] - x1, by[kt * ps] - y1, bz[kt * ps] - z1) : 0.f;
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+                const int k = kb + q8 * 32;
+                if (k < nt && !(dd[q8] != dd[q8]) && !(dts[q8] != dts[q8])) {
+                    const unsigned long long kk = pack_key(dd[q8], k);
+                    key = kk < key ? kk : key;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = shfl_xor_u64(key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0) {
+            const float d0 = sqdist_exact(bx[0] - x1, by[0] - y1, bz[0] - z1);
+            float dres;
+            int ires;
+            if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
+            else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
+            D.dist[(long long)u.cloud * D.nq + j] = dres;
+            D.idx[(long long)u.cloud * D.nq + j] = ires;
+            if (p.sums) atomicAdd(p.sums + u.cloud * 2 + D.slot, dres);
+            if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + u.cloud * 2 + D.slot, 1);
+        }
+    }
+}
+
 // DBG: instrumented build -- dumps every filter value to dbg[(unit*128 + row) * dbg_ld + target] when dbg != nullptr
 // (calibration / bring-up) and writes phase clocks to prof (tools/tc_phase_clocks.py) when prof != nullptr.
 template <bool DBG>
@@ -177,9 +239,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     float *sraw = reinterpret_cast<float *>(smem + kOffRaw);
     float *part = reinterpret_cast<float *>(smem + kOffPart);
     float *sq = reinterpret_cast<float *>(smem + kOffSq);
+    int *fb_list = reinterpret_cast<int *>(smem + kOffFb);
+    int *s_nfb = reinterpret_cast<int *>(smem + kOffMisc) + 1;
     float *s_wstat = reinterpret_cast<float *>(smem + kOffStat);
-    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + kHelpWarps;
-    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 2 * kHelpWarps;
+    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + 16;
+    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 32;
+    int *s_rawgroup = reinterpret_cast<int *>(smem + kOffStat) + 48;   // cloud/direction whose raw targets sraw[i] holds
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffMisc);
     volatile int *s_abort = reinterpret_cast<volatile int *>(smem + kOffMisc) + 2;
     const uint32_t sB_addr = smem_u32(smem + kOffB), sA_addr = smem_u32(smem + kOffA);
@@ -200,6 +265,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 4); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_ready + 8 * i, 1); mbar_init(bar_part + 8 * i, kScanWarps); }
         *s_abort = 0;
+        *s_nfb = 0;
+        s_rawgroup[0] = -1; s_rawgroup[1] = -1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -211,6 +278,115 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     if (tid == 0) stamp(1);
+
+    // Build the B operand of a cloud/direction from its raw targets in sraw[bsel] (already landed and visible to the
+    // team): centre, power-of-two scale, scaled split fp16 rows.  Called by a team of tn threads (tt = index in the team,
+    // tw = warp index in the team) with its own barrier; returns the frame (statistics valid after the caller's next
+    // team barrier via s_wstat / s_bstat).
+    auto build_b = [&](int nt, int bsel, int tt, int tn, int tw, auto &&team_bar, Frame &fr) {
+        const float *rx = sraw + (bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
+        float cx, cy, cz;
+        {   // centre of the filter frame: mean of up to 8 evenly spaced targets (any value is correct)
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            const int ns = nt < 8 ? nt : 8;
+            const int step = nt >> 3;
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+                if (s8 < ns) {
+                    const int k = nt < 8 ? s8 : s8 * step;
+                    sx += rx[k]; sy += ry[k]; sz += rz[k];
+                }
+            }
+            const float inv = 1.0f / (float)ns;
+            cx = sx * inv; cy = sy * inv; cz = sz * inv;
+        }
+        // pass 1: extent around the centre -> power-of-two scale
+        float cmax = 0.f;
+        int bad = 0;
+#pragma unroll 4
+        for (int k = tt; k < nt; k += tn) {
+            const float ax = fabsf(rx[k] - cx), ay = fabsf(ry[k] - cy), az = fabsf(rz[k] - cz);
+            bad |= !(ax < 1e18f) | !(ay < 1e18f) | !(az < 1e18f);
+            cmax = fmaxf(cmax, fmaxf(ax, fmaxf(ay, az)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        if (lane == 0) s_cstat[tw] = cmax;
+        team_bar();
+        cmax = 0.f;
+        for (int w = 0; w < tn / 32; ++w) cmax = fmaxf(cmax, s_cstat[w]);
+        float cs;
+        {
+            int e = (int)((__float_as_uint(cmax) >> 23) & 0xffu);   // biased exponent; 0 for cmax == 0 / subnormal
+            // Clouds smaller than 2^-60: the reference's own distances are subnormal there and round on an ABSOLUTE grid
+            // (2^-149), which the relative margin below does not cover -> every query of the cloud takes the exact scan.
+            bad |= e < 67;
+            e = e < 27 ? 27 : (e > 227 ? 227 : e);                   // keep s within [2^-101, 2^99]
+            cs = cmax > 0.f ? __uint_as_float((uint32_t)(253 - e) << 23) : 1.0f;   // 2^(126 - e): s*cmax in [0.5, 1)
+        }
+        // pass 2: scaled, split B operand
+        const int npad = ((nt + kTileN - 1) / kTileN) * kTileN;
+        float wmax = 0.f;
+        unsigned char *sBb = smem + kOffB + bsel * (kMaxT * 32);
+#pragma unroll 2
+        for (int k = tt; k < npad; k += tn) {
+            uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+            if (k < nt) {
+                const float x = (rx[k] - cx) * cs, y = (ry[k] - cy) * cs, z = (rz[k] - cz) * cs;
+                const float w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
+                bad |= !(w < 4.0f);
+                wmax = fmaxf(wmax, w);
+                unsigned short xh, xl, yh, yl, zh, zl;
+                split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
+                const __half hw1 = __float2half_rn(w);
+                const float wr = w - __half2float(hw1);
+                const __half hw2 = __float2half_rn(wr);
+                const __half hw3 = __float2half_rn(wr - __half2float(hw2));
+                v0 = make_uint4(pack2(xh, xl), pack2(xh, yh), pack2(yl, yh), pack2(zh, zl));
+                v1 = make_uint4(pack2(zh, __half_as_ushort(hw1)), pack2(__half_as_ushort(hw2), __half_as_ushort(hw3)), 0u, 0u);
+            } else {
+                v1.x = pack2(0, __half_as_ushort(__float2half_rn(kPadW)));
+            }
+            unsigned char *dst = sBb + (k >> 3) * 256 + (k & 7) * 16;
+            *reinterpret_cast<uint4 *>(dst) = v0;
+            *reinterpret_cast<uint4 *>(dst + 128) = v1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+            bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        }
+        if (lane == 0) { s_wstat[tw] = wmax; s_bstat[tw] = bad; }
+        fr.cx = cx; fr.cy = cy; fr.cz = cz; fr.cs = cs; fr.bsel = bsel;
+        fr.wmax = -1.f;   // statistics are picked up after the team's next barrier
+    };
+    auto pick_stats = [&](int nwarps, Frame &fr) {
+        float wmax = 0.f;
+        int bad = 0;
+        for (int w = 0; w < nwarps; ++w) { wmax = fmaxf(wmax, s_wstat[w]); bad |= s_bstat[w]; }
+        fr.wmax = wmax; fr.bad = bad;
+    };
+
+    // ---------------- prologue: the B operand of the first unit is built by the WHOLE CTA (everybody is idle anyway)
+    Frame fr0 = {0.f, 0.f, 0.f, 1.f, 0.f, 0, 0};
+    int group0 = -1;
+    if (nunits > 0) {
+        const Unit u = decode_unit(p, blk_begin);
+        const NNDirection &D = p.dir[u.d];
+        group0 = group_of(u);
+        const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp)
+            for (int k = tid; k < D.nt; k += kThreadsTC) cp_async4(sraw + comp * kMaxT + k, tb + k * D.t_ps + comp * D.t_cs);
+        cp_async_wait_all();
+        __syncthreads();
+        build_b(D.nt, 0, tid, kThreadsTC, warp, [] { __syncthreads(); }, fr0);
+        fence_async_smem();
+        __syncthreads();
+        pick_stats(kThreadsTC / 32, fr0);
+        if (tid == 0) s_rawgroup[0] = group0;
+    }
+    if (tid == 0) stamp(5);
 
     if (warp < kScanWarps) {
         // ================================================= scanners
@@ -307,8 +483,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     } else {
         // ================================================= helpers
         const int ht = tid - kHelp0, hw = warp - (kScanWarps + 1);
-        int st_group = -1, st_bsel = 1;      // cloud/direction of the most recently staged B operand; its buffer
-        Frame fr_st = {0.f, 0.f, 0.f, 1.f, 0.f, 0, 0};   // frame of the most recently staged unit
+        int st_group = group0, st_bsel = 0;  // cloud/direction of the most recently staged B operand; its buffer
+        Frame fr_st = fr0;                   // frame of the most recently staged unit
         float pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;   // raw query of the unit being staged (threads < 128), loaded early
         bool need_b = false;
 
@@ -345,82 +521,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const Unit u = decode_unit(p, blk_begin + ul);
             const NNDirection &D = p.dir[u.d];
             if (need_b) {
-                const int nt = D.nt;
-                const float *rx = sraw + (st_bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
                 cp_async_wait_all();
                 help_bar();   // every helper's raw targets have landed
-                float cx, cy, cz;
-                {   // centre of the filter frame: mean of up to 8 evenly spaced targets (any value is correct)
-                    float sx = 0.f, sy = 0.f, sz = 0.f;
-                    const int ns = nt < 8 ? nt : 8;
-                    const int step = nt >> 3;
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; ++s8) {
-                        if (s8 < ns) {
-                            const int k = nt < 8 ? s8 : s8 * step;
-                            sx += rx[k]; sy += ry[k]; sz += rz[k];
-                        }
-                    }
-                    const float inv = 1.0f / (float)ns;
-                    cx = sx * inv; cy = sy * inv; cz = sz * inv;
-                }
-                // pass 1: extent around the centre -> power-of-two scale
-                float cmax = 0.f;
-                int bad = 0;
-#pragma unroll 4
-                for (int k = ht; k < nt; k += kHelpThreads) {
-                    const float ax = fabsf(rx[k] - cx), ay = fabsf(ry[k] - cy), az = fabsf(rz[k] - cz);
-                    bad |= !(ax < 1e18f) | !(ay < 1e18f) | !(az < 1e18f);
-                    cmax = fmaxf(cmax, fmaxf(ax, fmaxf(ay, az)));
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-                if (lane == 0) s_cstat[hw] = cmax;
-                help_bar();
-                cmax = 0.f;
-#pragma unroll
-                for (int w = 0; w < kHelpWarps; ++w) cmax = fmaxf(cmax, s_cstat[w]);
-                float cs;
-                {
-                    int e = (int)((__float_as_uint(cmax) >> 23) & 0xffu);   // biased exponent; 0 for cmax == 0 / subnormal
-                    e = e < 27 ? 27 : (e > 227 ? 227 : e);                   // keep s within [2^-101, 2^99]
-                    cs = cmax > 0.f ? __uint_as_float((uint32_t)(253 - e) << 23) : 1.0f;   // 2^(126 - e): s*cmax in [0.5, 1)
-                }
-                // pass 2: scaled, split B operand
-                const int npad = ((nt + kTileN - 1) / kTileN) * kTileN;
-                float wmax = 0.f;
-                unsigned char *sBb = smem + kOffB + st_bsel * (kMaxT * 32);
-#pragma unroll 2
-                for (int k = ht; k < npad; k += kHelpThreads) {
-                    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-                    if (k < nt) {
-                        const float x = (rx[k] - cx) * cs, y = (ry[k] - cy) * cs, z = (rz[k] - cz) * cs;
-                        const float w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
-                        bad |= !(w < 4.0f);
-                        wmax = fmaxf(wmax, w);
-                        unsigned short xh, xl, yh, yl, zh, zl;
-                        split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
-                        const __half hw1 = __float2half_rn(w);
-                        const float wr = w - __half2float(hw1);
-                        const __half hw2 = __float2half_rn(wr);
-                        const __half hw3 = __float2half_rn(wr - __half2float(hw2));
-                        v0 = make_uint4(pack2(xh, xl), pack2(xh, yh), pack2(yl, yh), pack2(zh, zl));
-                        v1 = make_uint4(pack2(zh, __half_as_ushort(hw1)), pack2(__half_as_ushort(hw2), __half_as_ushort(hw3)), 0u, 0u);
-                    } else {
-                        v1.x = pack2(0, __half_as_ushort(__float2half_rn(kPadW)));
-                    }
-                    unsigned char *dst = sBb + (k >> 3) * 256 + (k & 7) * 16;
-                    *reinterpret_cast<uint4 *>(dst) = v0;
-                    *reinterpret_cast<uint4 *>(dst + 128) = v1;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-                    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-                }
-                if (lane == 0) { s_wstat[hw] = wmax; s_bstat[hw] = bad; }
-                fr_st.cx = cx; fr_st.cy = cy; fr_st.cz = cz; fr_st.cs = cs; fr_st.bsel = st_bsel;
-                fr_st.wmax = -1.f;   // statistics are picked up after the barrier below
+                build_b(D.nt, st_bsel, ht, kHelpThreads, hw, [] { help_bar(); }, fr_st);
+                if (ht == 0) s_rawgroup[st_bsel] = st_group;
             }
             if (ht < kQB) {
                 float *sqp = sq + (ul % 3) * 3 * kQB;
@@ -437,21 +541,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             fence_async_smem();
             help_bar();
             if (ht == 0) mbar_arrive(bar_ready + 8 * (ul & 1));
-            if (fr_st.wmax < 0.f) {
-                float wmax = 0.f;
-                int bad = 0;
-#pragma unroll
-                for (int w = 0; w < kHelpWarps; ++w) { wmax = fmaxf(wmax, s_wstat[w]); bad |= s_bstat[w]; }
-                fr_st.wmax = wmax; fr_st.bad = bad;
-            }
+            if (fr_st.wmax < 0.f) pick_stats(kHelpWarps, fr_st);
         };
 
         // resolve unit ul.  Warp hw owns the queries [hw*kQW, hw*kQW + kQW) of the unit:
         //   A  lane = query: merge the two scanner partials, margin test
         //   B  4 lanes per query: exact rescan of the best chunk (32 targets) from the raw targets in shared memory
-        //   C  whole warp per query: exact full scan for the queries that failed the margin test.  Reference semantics
-        //      incl. NaN: within a 512-target tile the first element is taken unconditionally and NaN never replaces or
-        //      is replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+        //   C  queries that fail the margin test go to the deferred list (exact full scan at the end of the kernel)
         constexpr int kQW = (kQB + kHelpWarps - 1) / kHelpWarps;   // 19
         auto resolve = [&](int ul, const Frame &fr) {
             const Unit u = decode_unit(p, blk_begin + ul);
@@ -477,18 +573,18 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const float x1 = sqp[ql], y1 = sqp[kQB + ql], z1 = sqp[2 * kQB + ql];
             const float ux = (x1 - fr.cx) * fr.cs, uy = (y1 - fr.cy) * fr.cs, uz = (z1 - fr.cz) * fr.cs;   // scaled frame
             const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
-            // Filter error bound E = 25u*S (u = 2^-24): frame 2u, |t'|^2 3u, operand splits 12u, tensor-core accumulation
-            // 8u (measured total on B200: <= 4.1u, tools/tc_calibrate.py).  The reference's argmin lies in the best chunk
-            // if second > best + 2E + 10u*S.
+            // Filter error bound E = 15u*S (u = 2^-24): frame 2u, |t'|^2 3u, operand splits 6u (3*2^-22 |q'||t'| and
+            // |q'||t'| <= S/2), tensor-core accumulation 4u (measured total on B200: <= 4.1u, tools/tc_calibrate.py).  The
+            // reference's argmin lies in the best chunk if second > best + 2E + 10u*S = 40u*S.
             //   S  = (|q'| + max|t'|)^2 bounds every target,
             //   S' = (2|q'| + rho)^2 bounds the targets that can compete (within rho of the query).
             const float qn = sqrtf(qq);
             const float rr = qn + sqrtf(fr.wmax);
             const float S = rr * rr;
-            const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 2.4e-6f * S);
+            const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 1.5e-6f * S);
             const float r2 = 2.0f * qn + rho;
             const float Seff = fminf(S, r2 * r2);
-            const float margin = __fmaf_rn(Seff, 3.7e-6f, 1e-36f);
+            const float margin = __fmaf_rn(Seff, 2.5e-6f, 1e-36f);
             const bool ok = live && !fr.bad && (qn < kQMax) && (b2 > b1 + margin);
             float ws = 0.f;   // fused epilogue accumulators of this lane
             int wc = 0;
@@ -536,48 +632,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     wc += dbest < p.fs_thr ? 1 : 0;
                 }
             }
-            // ---- C
-            unsigned fbm = __ballot_sync(0xffffffffu, live && !ok);
-            if (fbm != 0u && lane == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)__popc(fbm));
-            while (fbm != 0u) {
-                const int qi = __ffs(fbm) - 1;
-                fbm &= fbm - 1u;
-                const float xq = __shfl_sync(0xffffffffu, x1, qi), yq = __shfl_sync(0xffffffffu, y1, qi),
-                            zq = __shfl_sync(0xffffffffu, z1, qi);
-                const int jq = __shfl_sync(0xffffffffu, j, qi);
-                const bool nan_possible = fr.bad || !(fabsf(xq) < 1e18f) || !(fabsf(yq) < 1e18f) || !(fabsf(zq) < 1e18f);
-                unsigned long long key = ~0ull;
-#pragma unroll 4
-                for (int k = lane; k < nt; k += 32) {
-                    const float dd = sqdist_exact(rx[k] - xq, ry[k] - yq, rz[k] - zq);
-                    bool good = !(dd != dd);
-                    if (nan_possible) {
-                        const int kt = k & ~(kRefTile - 1);
-                        const float dts = sqdist_exact(rx[kt] - xq, ry[kt] - yq, rz[kt] - zq);
-                        good = good && !(dts != dts);
-                    }
-                    if (good) {
-                        const unsigned long long kk = pack_key(dd, k);
-                        key = kk < key ? kk : key;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = shfl_xor_u64(key, o);
-                    key = other < key ? other : key;
-                }
-                if (lane == 0) {
-                    const float d0 = sqdist_exact(rx[0] - xq, ry[0] - yq, rz[0] - zq);
-                    float dres;
-                    int ires;
-                    if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
-                    else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
-                    D.dist[(long long)u.cloud * D.nq + jq] = dres;
-                    D.idx[(long long)u.cloud * D.nq + jq] = ires;
-                    ws += dres;
-                    wc += dres < p.fs_thr ? 1 : 0;
-                }
-            }
+            // ---- C: the exact full scan of a query that failed the margin test is deferred to the end of the kernel
+            if (live && !ok) fb_list[atomicAdd(s_nfb, 1)] = (ul << 8) | ql | (fr.bad ? (1 << 30) : 0);
             if (p.sums != nullptr || p.fs_count != nullptr) {   // fused epilogues, one atomic per warp
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -609,6 +665,16 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             resolve(ul, f0);
             if (ht == 0) stamp(10 + ul * 6);
             help_bar();   // every helper is done with part/sq/sraw of unit ul before anything is restaged
+            {   // deferred exact scans: flush when the next unit could overflow the list
+                const int nfb = *s_nfb;
+                if (nfb > kFbCap - kQB) {
+                    run_fallbacks(p, blk_begin, fb_list, nfb, hw, kHelpWarps, lane, sraw, s_rawgroup);
+                    if (ht == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
+                    help_bar();
+                    if (ht == 0) *s_nfb = 0;
+                    help_bar();
+                }
+            }
             f0 = f1;
             if (stage_next) {
                 if (!issued) stage_issue(ul + 2);
@@ -620,9 +686,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         if (DBG && pf && ht == 0) pf[60] = a60;
     }
 
+    // ---------------- the deferred exact scans of this CTA, one warp per query, by every warp (measured faster than a
+    // CTA-wide scan per query: 41.5 vs 43.4 us at B=32, N=M=2048)
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) { stamp(3); stamp(4); }
+    if (tid == 0) stamp(3);
+    {
+        const int nfb = *s_nfb;
+        run_fallbacks(p, blk_begin, fb_list, nfb, warp, kThreadsTC / 32, lane, sraw, s_rawgroup);
+        if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
+    }
+    if (tid == 0) stamp(4);
     if (warp == kMmaWarp)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }

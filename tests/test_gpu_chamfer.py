@@ -8,10 +8,11 @@ from conftest import make_clouds
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 2], ids=["shared_block", "grouped"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "shared_block", "grouped", "tensor_core"], autouse=True)
 def nn_variant(request, pkg):
-    """Every test of this file runs against both NN forward kernels (psd_chamfer_nn_variant): the shared-block
-    kernel that small launches use and the grouped kernel that launches of >= 8 blocks per SM use."""
+    """Every test of this file runs against every NN forward kernel (psd_chamfer_nn_variant): the automatic choice, the
+    two FFMA kernels (shared-block, grouped) and the tcgen05 tensor-core kernel (clouds of <= 2048 points; larger
+    shapes fall through to the FFMA kernels)."""
     old = pkg._lib.lib.psd_chamfer_nn_variant(request.param)
     yield request.param
     pkg._lib.lib.psd_chamfer_nn_variant(old)

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(128, 1) umma_protocol(int mode, int iters, lon
 
 // Which property of the per-tile pattern is slow?  One thread issues `iters` kind::f16 M128 N128 K16 MMAs:
 //   rot  : 1 = rotate over the 4 TMEM buffers, 0 = always buffer 0      acc: accumulate flag      nb: B tiles in rotation
-__global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb, int iters, long long *cycles) {
+__global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb, int iters, long long *cycles, int commit_every = 0) {
+    __shared__ __align__(8) unsigned long long cbars[4];
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_s;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u) : "memory");
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&cbars[i])), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -180,6 +182,8 @@ __global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb,
             for (int i = 0; i < iters; ++i) {
                 const uint32_t d = tmem + (rot ? (i & 3) * 128 : 0);
                 asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d), "l"(ad), "l"(bd + (uint64_t)((i & (nb - 1)) * 256)), "r"(idesc), "r"((uint32_t)acc) : "memory");
+                if (commit_every > 0 && (i % commit_every) == commit_every - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&cbars[(i / commit_every) & 3])) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         }
@@ -193,6 +197,71 @@ __global__ void __launch_bounds__(128, 1) umma_pattern(int rot, int acc, int nb,
         const long long t1 = clock64();
         if (lane == 0) cycles[blockIdx.x] = t1 - t0;
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+
+// Handshake latencies.  mode 0: one thread: tcgen05.mma + commit, then try_wait until the commit lands (round trip).
+// mode 1: mbarrier ping-pong between lane 0 of warp 0 and lane 0 of warp 1 (arrive -> the other side's try_wait returns).
+// mode 2: like mode 1 but all 32 lanes of both warps poll (as the kernel's consumer warps do).
+__global__ void __launch_bounds__(128, 1) handshake(int mode, int iters, long long *cycles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ uint32_t tmem_s;
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[i])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_s;
+    const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]);
+    auto wait = [&](uint32_t bar, uint32_t parity) {
+        uint32_t ok = 0;
+        long long spins = 0;
+        while (!ok && spins < 20000000LL) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            ++spins;
+        }
+    };
+    const long long t0 = clock64();
+    if (mode == 0) {
+        if (warp == 0 && lane == 0) {
+            Cfg c = {0, 128, 256, 0, 4096, 128, 1, 1};
+            const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t ad = make_desc(smem_u32(smem), c), bd = make_desc(smem_u32(smem) + 8192, c);
+            for (int i = 0; i < iters; ++i) {
+                asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(0u) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(b0) : "memory");
+                wait(b0, (uint32_t)(i & 1));
+            }
+        }
+    } else {
+        const bool poll = mode == 2 || lane == 0;
+        if (warp == 0 && poll) {
+            for (int i = 0; i < iters; ++i) {
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b0) : "memory");
+                wait(b1, (uint32_t)(i & 1));
+            }
+        } else if (warp == 1 && poll) {
+            for (int i = 0; i < iters; ++i) {
+                wait(b0, (uint32_t)(i & 1));
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b1) : "memory");
+            }
+        }
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
@@ -264,5 +333,29 @@ int main() {
                 printf("pattern: rotate D=%d accumulate=%d B tiles=%2d  %8.1f cycles per MMA\n", rot, acc, nb, mean / 148 / 2000);
                 fflush(stdout);
             }
+    for (int ce = 1; ce <= 8; ce *= 2) {
+        for (int rep = 0; rep < 2; ++rep) {
+            umma_pattern<<<148, 128, 200 * 1024>>>(1, 0, 16, 2000, d_cyc, ce);
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h_cyc, d_cyc, sizeof(h_cyc), cudaMemcpyDeviceToHost));
+        double mean = 0;
+        for (int i = 0; i < 148; ++i) mean += h_cyc[i];
+        printf("pattern: commit (nobody waits) after every %d MMA(s): %8.1f cycles per MMA\n", ce, mean / 148 / 2000);
+        fflush(stdout);
+    }
+    CK(cudaFuncSetAttribute(handshake, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    const char *hn[] = {"MMA + commit + wait round trip (one thread)", "mbarrier ping-pong, one lane per side (2 hops)", "mbarrier ping-pong, 32 lanes poll (2 hops)"};
+    for (int mode = 0; mode < 3; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            handshake<<<148, 128, 64 * 1024>>>(mode, 2000, d_cyc);
+            CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h_cyc, d_cyc, sizeof(h_cyc), cudaMemcpyDeviceToHost));
+        double mean = 0;
+        for (int i = 0; i < 148; ++i) mean += h_cyc[i];
+        printf("handshake: %-50s %8.1f cycles per iteration\n", hn[mode], mean / 148 / 2000);
+        fflush(stdout);
+    }
     return 0;
 }

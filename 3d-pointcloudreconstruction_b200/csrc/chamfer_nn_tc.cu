@@ -3,7 +3,7 @@
 // Same contract and the same exactness scheme as chamfer.cu (reference: metric/chamfer3D/chamfer3D.cu:12-154):
 // dist/idx always come from the reference's exact formula; a filter only decides where to look.  Here the filter
 //     a_k = |t_k - c|^2 - 2 (q - c).(t_k - c)            ( = |t_k - q|^2 - |q - c|^2 )
-// is a [128 queries] x [128 targets] x K=16 FP16 GEMM per tile: ONE tcgen05.mma.kind::f16 issued by one thread.
+// is a [128 queries] x [256 targets] x K=16 FP16 GEMM per tile: ONE tcgen05.mma.kind::f16 issued by one thread.
 // fp32-class accuracy comes from (1) a per-cloud power-of-two scale s that brings max|t-c| into [0.5,1) -- exact in
 // fp32, keeps every term inside the fp16 exponent range -- and (2) splitting every operand into two fp16 terms
 // (hi + lo, 22 significand bits) and |t-c|^2 into three, laid out along K so that the cross terms line up:
@@ -12,12 +12,12 @@
 // (products of two 11-bit significands are exact in the fp32 accumulator; the dropped ql*tl terms and the split
 // residues are bounded by 3*2^-22 |q'||t'|).  Measured on B200 (tools/ubench_umma.cu): kind::f16 M128 N128 K16 issues
 // every 64 cycles, kind::tf32 K8 only every 96, independent of the shared-memory layout -- hence fp16 and one
-// instruction per tile.  Accumulators live in TMEM (4 buffers of 128 columns).
+// instruction per tile (N = 256: 128 cycles).  Accumulators live in TMEM (2 buffers of 256 columns).
 //
 // One persistent CTA per SM, three concurrent roles (no CTA-wide barrier in the steady state):
 //   * warps 0-7   SCANNERS: warp w reads TMEM lanes 32*(w%4).. (one thread = one query row, so the running minimum
-//                 needs no cross-lane traffic) of the tiles of column group w/4 with tcgen05.ld.32x32b.x32, double
-//                 buffered, and keeps per 32-target chunk (best chunk minimum, its chunk id, second best): 16 min
+//                 needs no cross-lane traffic), columns 128*(w/4).. of every tile with tcgen05.ld.32x32b.x32, 64
+//                 columns at a time, and keeps per 32-target chunk (best chunk minimum, its chunk id, second best): 16 min
 //                 instructions + 6 ALU ops per 32 pairs instead of 96 FFMA + 16 FMNMX3 in the FFMA kernel.
 //   * warp  8     MMA issuer: waits for operands (ready mbarrier) and a free TMEM buffer (empty mbarrier), issues one
 //                 tcgen05.mma per tile and commits it to the buffer's full mbarrier.
@@ -40,8 +40,11 @@ constexpr int kHelpWarps = 7;                   // 16 warps in all: 4 per sub-pa
 constexpr int kHelpThreads = kHelpWarps * 32;
 constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
 constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 512
-constexpr int kTileN = 128;                     // targets per MMA tile = TMEM buffer width (columns)
-constexpr int kBufs = 4;                        // TMEM buffers: 4 x 128 columns = all 512
+constexpr int kTileN = 256;                     // targets per MMA tile = TMEM buffer width (columns)
+constexpr int kBufs = 512 / kTileN;             // TMEM buffers: all 512 columns.  Two 256-column tiles beat four 128-column
+                                                // ones (37.4 vs 41.5 us at B=32, N=M=2048): the mbarrier / tcgen05.commit round
+                                                // trip per tile (~300-400 cycles, tools/ubench_pipe.cu) is paid half as often
+constexpr int kBufShift = 1;                    // log2(kBufs)
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
 constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value
@@ -114,7 +117,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) |
            (1ull << 46);
 }
-// kind::f16, D = F32, A/B = F16 (format 0), both K-major, M = 128, N = 128
+// kind::f16, D = F32, A/B = F16 (format 0), both K-major, M = 128, N = kTileN
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     if (tid == 0) stamp(0);
 
     if (tid == 0) {
-        for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 4); }
+        for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, kScanWarps); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_ready + 8 * i, 1); mbar_init(bar_part + 8 * i, kScanWarps); }
         *s_abort = 0;
         *s_nfb = 0;
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 
     if (warp < kScanWarps) {
         // ================================================= scanners
-        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column group (tiles with g % 2 == c)
+        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column half of every tile
         const int row = r * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(r * 32) << 16);
         int g0 = 0;
@@ -407,35 +410,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 best = fminf(best, m);
                 bchunk = lt ? cid : bchunk;
             };
-            for (int t = (c - g0) & 1; t < ntiles; t += 2) {
+            // every scanner warp takes its half (columns c*128 .. c*128+127) of every 256-column tile
+            for (int t = 0; t < ntiles; ++t) {
                 const int gg = g0 + t;
                 const int b = gg & (kBufs - 1);
                 const long long w0 = DBG ? clock64() : 0;
-                mbar_wait(bar_full + 8 * b, (gg >> 2) & 1, s_abort);
+                mbar_wait(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
                 if (DBG) a59 += clock64() - w0;
                 tc_fence_after();
-                const uint32_t ta = tlane + (uint32_t)(b * kTileN);
+                const int col0 = c * 128;                              // first column of this warp's share of the tile
+                const uint32_t ta = tlane + (uint32_t)(b * kTileN + col0);
+                const int cid0 = (t * kTileN + col0) / kCh;            // chunk id of the first 32 columns
                 uint32_t ra[32], rb[32];
                 tmem_ld64_wait(ta, ra, rb);
                 if (DBG && dbg) {
-                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN;
+                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
                 }
-                chunk(ra, t * 4);
-                chunk(rb, t * 4 + 1);
+                chunk(ra, cid0);
+                chunk(rb, cid0 + 1);
                 tmem_ld64_wait(ta + 64, ra, rb);
-                // every column of the tile is in registers: hand the TMEM buffer back before the remaining min work
+                // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty + 8 * b);
                 if (DBG && dbg) {
-                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64;
+                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
                 }
-                chunk(ra, t * 4 + 2);
-                chunk(rb, t * 4 + 3);
+                chunk(ra, cid0 + 2);
+                chunk(rb, cid0 + 3);
             }
             g0 += ntiles;
             {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const int b = g & (kBufs - 1);
                     w0 = DBG ? clock64() : 0;
-                    mbar_wait(bar_empty + 8 * b, ((g >> 2) & 1) ^ 1, s_abort);
+                    mbar_wait(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
                     if (DBG) a57 += clock64() - w0;
                     tc_fence_after();
                     const long long w1 = DBG ? clock64() : 0;

@@ -29,7 +29,7 @@ vp = lambda t: ctypes.c_void_p(t.data_ptr())
 def run_dump(x, y):
     b, n, _ = x.shape
     m = y.shape[1]
-    ld = ((max(n, m) + 127) // 128) * 128
+    ld = ((max(n, m) + 255) // 256) * 256   # the kernel dumps whole 256-column tiles
     units = b * ((n + 127) // 128 + (m + 127) // 128)
     dump = torch.full((units * 128, ld), float("nan"), device=dev)
     d1 = torch.empty(b, n, device=dev); d2 = torch.empty(b, m, device=dev)

@@ -13,10 +13,10 @@ from . import chamfer_3D, emd  # native-module mirrors (pybind names of the refe
 from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction
 from .emd_module import emdFunction, emdModule
 from .fscore import fscore, chamfer_fscore_fused
-from .loss import Loss
+from .loss import Loss, chamfer_loss_step_host
 from .metrics import Metrics
 
 __all__ = [
     "chamfer_3D", "emd", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
-    "fscore", "chamfer_fscore_fused", "Loss", "Metrics",
+    "fscore", "chamfer_fscore_fused", "Loss", "chamfer_loss_step_host", "Metrics",
 ]

@@ -461,6 +461,10 @@ struct GradParams {
     int b, n, m;
     long long total1;  // b*n
     long long total;   // b*(n+m)
+    // mean-loss mode (gd1 == gd2 == nullptr): graddist1[e] = *upstream / cnt1, graddist2[e] = *upstream / cnt2 -- what
+    // autograd hands to the reference's backward for loss = mean(dist1) + mean(dist2) (loss/loss.py:36)
+    const float *upstream;
+    float cnt1, cnt2;
 };
 
 __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
@@ -481,7 +485,8 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
     if (active) {
         const long long cloud = e / na;
         const int j2 = idx[e];
-        const float g = gd[e] * 2.0f;
+        const float gdv = gd ? gd[e] : __fdiv_rn(p.upstream ? *p.upstream : 1.0f, d2 ? p.cnt2 : p.cnt1);
+        const float g = gdv * 2.0f;
         const float *pa = a + e * 3;
         tgt = cloud * nb + j2;
         const float *pb = bq + tgt * 3;
@@ -516,6 +521,16 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
         atomicAdd(o + 1, -sy);
         atomicAdd(o + 2, -sz);
     }
+}
+
+// loss = sum_b sums[b,0] / cnt1 + sum_b sums[b,1] / cnt2 -- the epilogue of Loss.get_chamfer_loss (loss/loss.py:36) on
+// the per-cloud sums that the forward kernels accumulate; one warp, fixed summation order.
+__global__ void chamfer_mean_loss_kernel(const float *__restrict__ sums, int b, float cnt1, float cnt2, float *__restrict__ out) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < b; i += 32) { s1 += sums[2 * i]; s2 += sums[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (threadIdx.x == 0) *out = __fdiv_rn(s1, cnt1) + __fdiv_rn(s2, cnt2);
 }
 
 }  // namespace psd
@@ -622,11 +637,17 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     return cudaGetLastError();
 }
 
+cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m, float *out, cudaStream_t stream) {
+    chamfer_mean_loss_kernel<<<1, 32, 0, stream>>>(sums, b, (float)((long long)b * n), (float)((long long)b * m), out);
+    return cudaGetLastError();
+}
+
 cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
-                                        int b, int n, int m, cudaStream_t stream) {
+                                        int b, int n, int m, cudaStream_t stream, const float *upstream) {
     if (b <= 0 || (n <= 0 && m <= 0)) return cudaSuccess;
     GradParams p;
+    p.upstream = upstream; p.cnt1 = (float)((long long)b * n); p.cnt2 = (float)((long long)b * m);
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.g1 = gradxyz1; p.g2 = gradxyz2; p.gd1 = graddist1; p.gd2 = graddist2;
     p.idx1 = idx1; p.idx2 = idx2; p.b = b; p.n = n; p.m = m;
     p.total1 = (long long)b * n;

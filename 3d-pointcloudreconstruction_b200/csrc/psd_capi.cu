@@ -11,7 +11,8 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
                                        int *fs_count, int q_begin, int q_count, cudaStream_t stream);
 cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
-                                        int b, int n, int m, cudaStream_t stream);
+                                        int b, int n, int m, cudaStream_t stream, const float *upstream = nullptr);
+cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m, float *out, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
 int psd_set_nn_variant(int v);
 void psd_set_tc_debug(float *dbg, int ld);
@@ -118,6 +119,25 @@ int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const
     return finish("psd_emd_backward", psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, (cudaStream_t)stream));
 }
 
+int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                                  float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, void *stream) {
+    if (layout != 0 && layout != 1) {
+        psd_set_error_msg("psd_chamfer_mean_loss_forward: layout must be 0 ([B,N,3]) or 1 ([B,3,N])");
+        return -1;
+    }
+    cudaError_t e = psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums_zeroed, 0.f, nullptr,
+                                               0, -1, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(sums_zeroed, b, n, m, loss, (cudaStream_t)stream);
+    return finish("psd_chamfer_mean_loss_forward", e);
+}
+
+int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                   const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream) {
+    return finish("psd_chamfer_mean_loss_backward",
+                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, nullptr, nullptr, idx1, idx2, b, n, m,
+                                              (cudaStream_t)stream, upstream));
+}
+
 int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }
 
 int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
@@ -143,6 +163,7 @@ int psd_chamfer_stats(long long *out_host2, int reset) {
 }
 
 // ---- host-buffer entry point: stage through a grow-only device workspace owned by the library
+// (two workspaces: forward-only and training-step)
 static float *g_ws = nullptr;
 static size_t g_ws_bytes = 0;
 
@@ -172,6 +193,56 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
         (e = cudaMemcpyAsync(idx2_host, d_i2, sizeof(int) * s2, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
         return finish("psd_chamfer_forward_host(D2H)", e);
     return finish("psd_chamfer_forward_host(sync)", cudaStreamSynchronize(stream));
+}
+
+
+// fwd + fused mean loss + bwd of one training step with HOST inputs: the end-to-end form of Loss.get_chamfer_loss
+// (loss/loss.py:30-37) followed by loss.backward().  Gradients stay on the device unless host pointers are given.
+static float *g_ws2 = nullptr;
+static size_t g_ws2_bytes = 0;
+int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                               float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                               void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
+    // layout: xyz1 | xyz2 | grad1 | grad2 | dist1 | dist2 | idx1 | idx2 | sums[2b] | loss
+    const size_t nfloat = 6 * (s1 + s2) + 2 * (s1 + s2) + 2 * (size_t)b + 4;
+    const size_t need = sizeof(float) * nfloat;
+    if (need > g_ws2_bytes) {
+        if (g_ws2) cudaFree(g_ws2);
+        g_ws2 = nullptr; g_ws2_bytes = 0;
+        cudaError_t e = cudaMalloc(&g_ws2, need);
+        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(cudaMalloc)", e);
+        g_ws2_bytes = need;
+    }
+    float *d_x1 = g_ws2, *d_x2 = d_x1 + 3 * s1, *d_g1 = d_x2 + 3 * s2, *d_g2 = d_g1 + 3 * s1;
+    float *d_d1 = d_g2 + 3 * s2, *d_d2 = d_d1 + s1;
+    int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
+    float *d_sums = reinterpret_cast<float *>(d_i2 + s2), *d_loss = d_sums + 2 * (size_t)b;
+    cudaError_t e;
+    // the two clouds are adjacent in the workspace: one copy when they are adjacent on the host too
+    if (xyz2_host == xyz1_host + 3 * s1) {
+        e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * (s1 + s2), cudaMemcpyHostToDevice, stream);
+    } else {
+        e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x2, xyz2_host, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
+    }
+    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(H2D)", e);
+    // gradients and per-cloud sums start from zero: one memset each (grad1|grad2 are adjacent)
+    if ((e = cudaMemsetAsync(d_g1, 0, sizeof(float) * 3 * (s1 + s2), stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(d_sums, 0, sizeof(float) * (2 * (size_t)b + 1), stream)) != cudaSuccess)
+        return finish("psd_chamfer_loss_step_host(memset)", e);
+    e = psd_launch_chamfer_forward(d_x1, d_x2, b, n, m, 0, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream);
+    if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(d_sums, b, n, m, d_loss, stream);
+    if (e == cudaSuccess) e = psd_launch_chamfer_backward(d_x1, d_x2, d_g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, stream, nullptr);
+    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(launch)", e);
+    e = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && gradxyz1_host) e = cudaMemcpyAsync(gradxyz1_host, d_g1, sizeof(float) * 3 * s1, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && gradxyz2_host) e = cudaMemcpyAsync(gradxyz2_host, d_g2, sizeof(float) * 3 * s2, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(D2H)", e);
+    if (gradxyz1_dev) *gradxyz1_dev = d_g1;
+    if (gradxyz2_dev) *gradxyz2_dev = d_g2;
+    return finish("psd_chamfer_loss_step_host(sync)", cudaStreamSynchronize(stream));
 }
 
 }  // extern "C"

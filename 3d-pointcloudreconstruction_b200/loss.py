@@ -5,9 +5,50 @@ import torch.nn as nn
 try:
     from .dist_chamfer_3D import chamfer_3DDist
     from . import emd_module as emd_func
+    from . import _lib
 except ImportError:
     from dist_chamfer_3D import chamfer_3DDist
     import emd_module as emd_func
+    import _lib
+
+
+class _ChamferMeanLoss(torch.autograd.Function):
+    """mean(dist1) + mean(dist2) (loss/loss.py:35-36) as ONE forward launch (+ a one-warp reduction) and ONE backward
+    launch: the per-cloud sums come from the NN kernel's epilogue and the constant gradients 1/(B*N), 1/(B*M) are formed
+    inside the backward kernel (psd_chamfer_mean_loss_forward / _backward).  Results agree with the unfused path to fp32
+    summation-order noise (the sums are accumulated with float atomics)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        dev = xyz1.device
+        fbuf = torch.empty(b * (n + m), device=dev, dtype=torch.float32)
+        ibuf = torch.empty(b * (n + m), device=dev, dtype=torch.int32)
+        small = torch.zeros(2 * b + 1, device=dev, dtype=torch.float32)      # per-cloud sums [B,2] + the loss scalar
+        idx1, idx2 = ibuf[: b * n], ibuf[b * n:]
+        with torch.cuda.device(dev):
+            rc = _lib.lib.psd_chamfer_mean_loss_forward(
+                _lib.ptr(xyz1), _lib.ptr(xyz2), b, n, m, 0, _lib.ptr(fbuf), _lib.ptr(fbuf[b * n:]), _lib.ptr(idx1),
+                _lib.ptr(idx2), _lib.ptr(small), _lib.ptr(small[2 * b:]), _lib.stream_of(xyz1))
+        _lib.raise_on_cuda_error(rc, "psd_chamfer_mean_loss_forward")
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        return small[2 * b]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        up = grad_loss.contiguous().to(torch.float32)
+        buf = torch.zeros(xyz1.numel() + xyz2.numel(), device=xyz1.device, dtype=torch.float32)
+        g1 = buf[: xyz1.numel()].view(xyz1.shape)
+        g2 = buf[xyz1.numel():].view(xyz2.shape)
+        with torch.cuda.device(xyz1.device):
+            rc = _lib.lib.psd_chamfer_mean_loss_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(up),
+                                                         _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, _lib.stream_of(xyz1))
+        _lib.raise_on_cuda_error(rc, "psd_chamfer_mean_loss_backward")
+        return g1, g2
 
 
 class Loss(nn.Module):
@@ -25,5 +66,29 @@ class Loss(nn.Module):
 
     def get_chamfer_loss(self, pred, gt):
         """pred, gt: [B, N, 3].  mean(dist1) + mean(dist2) (loss/loss.py:35-36)."""
+        if (pred.is_cuda and gt.is_cuda and pred.dtype == torch.float32 and gt.dtype == torch.float32 and pred.dim() == 3
+                and gt.dim() == 3 and pred.shape[0] == gt.shape[0] and pred.numel() > 0 and gt.numel() > 0):
+            return _ChamferMeanLoss.apply(pred.contiguous(), gt.contiguous())   # fused epilogue + scalar-gradient backward
         dist1, dist2, _, _ = self._cham(pred, gt)
         return torch.mean(dist1) + torch.mean(dist2)
+
+
+def chamfer_loss_step_host(pred_host, gt_host, want_grads=False, stream=None):
+    """One training step of Loss.get_chamfer_loss with HOST tensors (float32, contiguous, ideally pinned) through the
+    C ABI's host-buffer entry point psd_chamfer_loss_step_host: H2D, forward, fused mean loss, backward, loss read back.
+    Returns the loss as a Python float (and the two gradients as host tensors if want_grads)."""
+    import ctypes
+    assert not pred_host.is_cuda and not gt_host.is_cuda and pred_host.dtype == torch.float32 and gt_host.dtype == torch.float32
+    pred_host = pred_host.contiguous(); gt_host = gt_host.contiguous()
+    b, n, _ = pred_host.shape
+    m = gt_host.shape[1]
+    loss = ctypes.c_float(0.0)
+    g1 = torch.empty_like(pred_host) if want_grads else None
+    g2 = torch.empty_like(gt_host) if want_grads else None
+    s = stream if stream is not None else torch.cuda.current_stream()
+    rc = _lib.lib.psd_chamfer_loss_step_host(
+        ctypes.c_void_p(pred_host.data_ptr()), ctypes.c_void_p(gt_host.data_ptr()), b, n, m, ctypes.byref(loss),
+        ctypes.c_void_p(g1.data_ptr()) if want_grads else None, ctypes.c_void_p(g2.data_ptr()) if want_grads else None,
+        None, None, ctypes.c_void_p(s.cuda_stream))
+    _lib.raise_on_cuda_error(rc, "psd_chamfer_loss_step_host")
+    return (loss.value, g1, g2) if want_grads else loss.value

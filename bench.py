@@ -16,9 +16,12 @@ Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
                ("inputs larger than L2"), so inputs are read from HBM.
 `e2e`        : the same metric through the public API (chamfer_3DDist()(xyz1, xyz2) + .backward()), with the
                step's inputs copied from pinned host memory and the loss read back on the host every step.
-`roofline`   : dominant kernel chamfer_nn_kernel, algorithmic 8 flop per directed pair,
+`roofline`   : dominant kernel chamfer_nn_tc_kernel, algorithmic 8 flop per directed pair,
                duration = CUDA events around back-to-back launches, peak = FP32 FMA rate measured live by an
                FFMA-only kernel (MEASURED_PEAKS.json has no FP32 entry; nominal 74.45 TFLOP/s also given).
+               The kernel evaluates the pairs as a split-fp16 K=16 GEMM on the tensor cores (tcgen05) and is bound
+               by the min-reduction on the ALU pipe and the TMEM hand-shake, so `roofline.tensor` adds the issued
+               tensor flops against MEASURED_PEAKS.json's bf16 figure.
 `cpu_baseline`: the oracle's C restatement of the same step on the host cores (bounded sample).
 --impl reference: the reference's own CPU implementation of the path (its pure-torch chamfer,
                loss/loss_.py:66-91, restated in oracle/oracle.py) on the host cores, bounded sample per step.
@@ -39,6 +42,7 @@ sys.path.insert(0, ROOT)
 B, N, M = 32, 2048, 2048
 EMD_EPS, EMD_ITERS = 0.005, 50
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.45
+TRAFFIC_BYTES = 1.6e6   # dram bytes per chamfer forward launch, from the committed ncu capture (profiles/)
 
 
 def parse():
@@ -242,17 +246,34 @@ def main():
     value = world * pairs_step * K / (ms_total * 1e-3)
 
     # ---- end to end through the public API with host buffers
-    cham = pkg.chamfer_3DDist()
-    hx = [torch.rand(B, N, 3, generator=g).pin_memory() for _ in range(4)]
-    hy = [torch.rand(B, M, 3, generator=g).pin_memory() for _ in range(4)]
+    # End to end through the C ABI's host-buffer entry point of the path's caller, Loss.get_chamfer_loss + backward
+    # (loss/loss.py:30-37): psd_chamfer_loss_step_host copies the step's clouds from pinned host memory, runs forward,
+    # fused mean loss and backward, and returns the loss on the host (gradients stay on the device for the caller's
+    # own backward).  Both clouds of a step live in one pinned buffer [B*(N+M), 3] -> one H2D copy per step.
+    hxy = [torch.rand(B * (N + M), 3, generator=g).pin_memory() for _ in range(4)]
+    hviews = [(h[: B * N].view(B, N, 3), h[B * N:].view(B, M, 3)) for h in hxy]
 
     def e2e_step(s):
-        a = hx[s % 4].to(dev, non_blocking=True).requires_grad_(True)
-        b_ = hy[s % 4].to(dev, non_blocking=True).requires_grad_(True)
-        o1, o2, _, _ = cham(a, b_)
-        loss = torch.mean(o1) + torch.mean(o2)
+        a, b_ = hviews[s % 4]
+        return pkg.chamfer_loss_step_host(a, b_)   # H2D + fwd + loss + bwd + D2H(loss) + sync
+
+    def e2e_step_torch(s):   # the same step through the torch-facing module API (reported as e2e.torch_api)
+        xy = hxy[s % 4].to(dev, non_blocking=True)
+        a = xy[: B * N].view(B, N, 3).requires_grad_(True)
+        b_ = xy[B * N:].view(B, M, 3).requires_grad_(True)
+        loss = loss_mod.get_chamfer_loss(a, b_)
         loss.backward()
-        return loss.item()  # device -> host read of the step's result
+        return loss.item()
+
+    loss_mod = pkg.Loss()
+    for s in range(W):
+        e2e_step_torch(s)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(50):
+        e2e_step_torch(s)
+    torch.cuda.synchronize()
+    e2e_torch_value = world * 2.0 * B * N * M * 50 / (time.perf_counter() - t0)
 
     Ke = min(K, 200)
     for s in range(W):
@@ -279,8 +300,9 @@ def main():
                    "timing": "K steps captured in one CUDA graph, CUDA events on the launch stream, max over ranks",
                    "parallelism": f"batch-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 4 * 3 * B * (N + M), "d2h_bytes_per_step": 4,
-                "steps": Ke, "api": "chamfer_3DDist()(xyz1, xyz2); (mean(d1)+mean(d2)).backward(); loss.item()"},
-        "gpu_launches": 2 * K,
+                "steps": Ke, "api": "psd_chamfer_loss_step_host (C ABI, pinned host buffers): H2D + chamfer fwd + mean loss [loss/loss.py:36] + bwd + D2H loss + sync",
+                "torch_api": {"value": e2e_torch_value, "unit": "pairs/s", "api": "Loss().get_chamfer_loss(pred, gt); loss.backward(); loss.item() with a pinned-host H2D copy per step"}},
+        "gpu_launches": 2 * K,   # value leg: chamfer_nn_tc_kernel + chamfer_grad_kernel per step (e2e adds chamfer_mean_loss_kernel)
         "clocks": sampler.result(),
     }
 
@@ -316,12 +338,19 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        issued_tensor = 2.0 * 16 * pairs_step / (fwd_ms * 1e-3) / 1e12   # K = 16 MACs per pair on the tensor pipe
+        tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
         out["roofline"] = {
-            "bound": "fp32_fma", "kernel": "chamfer_nn_kernel", "achieved": achieved, "peak": float(tf.value),
+            "bound": "fp32_fma", "kernel": "chamfer_nn_tc_kernel", "achieved": achieved, "peak": float(tf.value),
             "unit": "TFLOP/s", "frac": achieved / float(tf.value), "peak_source": "measured live: FFMA-only kernel on all SMs (psd_fp32_fma_peak)",
             "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS,
             "algorithmic": "8 flop per directed pair x 2*B*N*M pairs per launch", "us_per_launch": fwd_ms * 1e3,
-            "traffic": 1.6e6, "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); inputs 1.57 MB",
+            "traffic": TRAFFIC_BYTES, "traffic_note": "dram__bytes_read+write per launch from profiles/ (ncu --set full); inputs 1.57 MB",
+            "note": "pair work runs as a split-fp16 GEMM on tcgen05 tensor cores; 8 flop/pair is the reference formulation's count, "
+                    "so the fraction is 'FP32-FMA-equivalent' and may exceed what an FFMA kernel can reach (the FFMA kernel of this "
+                    "library: 0.53)",
+            "tensor": {"issued_tflops": issued_tensor, "peak": tensor_peak, "frac": issued_tensor / tensor_peak,
+                       "what": "32 fp16 flop per pair (K=16) issued with tcgen05.mma kind::f16; peak = MEASURED_PEAKS.json bf16_tflops"},
         }
         bwd_bytes = 4.0 * (3 * B * (N + M)) + 8.0 * B * (N + M) + 4.0 * (3 * B * (N + M))
         out["roofline_bwd"] = {

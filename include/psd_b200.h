@@ -103,11 +103,33 @@ int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const
                      int b, int n, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused training loss of the hot path's caller: Loss.get_chamfer_loss (loss/loss.py:30-37) =
+ * mean(dist1) + mean(dist2) over chamfer_3DDist's outputs.  Forward: the NN kernel accumulates per-cloud sums in its
+ * epilogue (sums_zeroed[B,2], zero-filled by the caller) and a one-warp kernel reduces them to the scalar *loss (device);
+ * dist/idx are still written.  Backward: what autograd would hand to psd_chamfer_backward for this loss, graddist1 =
+ * *upstream/(B*N), graddist2 = *upstream/(B*M), is formed inside the kernel from the device scalar `upstream`
+ * (NULL = 1.0), so no gradient tensors are materialised; gradxyz1/gradxyz2 must be zero-filled by the caller.
+ * Same return convention as above. */
+int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                                  float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, void *stream);
+int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                   const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
  * stages them through its own device workspace on `stream` and copies the results back).
  * ------------------------------------------------------------------------------------------- */
 int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *dist1_host,
                              float *dist2_host, int *idx1_host, int *idx2_host, void *stream);
+
+/* One training step of the chamfer loss with HOST inputs (pinned or pageable): H2D of both clouds (one copy when
+ * xyz2_host == xyz1_host + 3*b*n), forward, fused mean loss (loss/loss.py:36), backward of that loss (upstream 1.0), the
+ * scalar loss copied to *loss_host, then a stream synchronise.  Gradients are copied to gradxyz1_host / gradxyz2_host
+ * when those are non-NULL; *gradxyz1_dev / *gradxyz2_dev (when non-NULL) receive the device pointers of the gradients,
+ * valid until the next call (they feed the caller's own backward on the device).  Same return convention. */
+int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                               float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                               void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py; not part of the reference surface).

@@ -107,6 +107,49 @@ def test_backward_matches_oracle(pkg, oracle, cuda):
             assert np.abs(got - want).max() <= tol, (kind, np.abs(got - want).max(), tol)
 
 
+def test_fused_mean_loss_matches_unfused_and_oracle(pkg, oracle, cuda):
+    """Loss.get_chamfer_loss (loss/loss.py:30-37) on the fused path: loss within 1e-5 relative of mean(d1)+mean(d2)
+    from the oracle, gradients within 1e-5 relative of the oracle's backward fed with autograd's constant gradients
+    1/(B*N), 1/(B*M) scaled by an upstream factor."""
+    b, n, m = 3, 700, 1100
+    x, y = make_clouds("uniform", b, n, m, seed=77)
+    tx = torch.from_numpy(x).to(cuda).requires_grad_(True)
+    ty = torch.from_numpy(y).to(cuda).requires_grad_(True)
+    loss = pkg.Loss().get_chamfer_loss(tx, ty)
+    (3.0 * loss).backward()
+    torch.cuda.synchronize()
+    d1, d2, i1, i2 = oracle.chamfer_forward(x, y, nthreads=8)
+    want = d1.astype(np.float64).mean() + d2.astype(np.float64).mean()
+    assert abs(float(loss) - want) <= 1e-5 * abs(want)
+    gd1 = np.full((b, n), np.float32(3.0) / np.float32(b * n), np.float32)
+    gd2 = np.full((b, m), np.float32(3.0) / np.float32(b * m), np.float32)
+    g1, g2 = oracle.chamfer_backward(x, y, gd1, gd2, i1, i2)
+    for got, ref in ((tx.grad.cpu().numpy(), g1), (ty.grad.cpu().numpy(), g2)):
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 1e-5 * scale
+    # and the unfused public path gives the same loss
+    o1, o2, _, _ = pkg.chamfer_3DDist()(tx.detach(), ty.detach())
+    unfused = float(torch.mean(o1) + torch.mean(o2))
+    assert abs(float(loss) - unfused) <= 1e-5 * abs(unfused)
+
+
+def test_host_buffer_loss_step(pkg, oracle, cuda):
+    """psd_chamfer_loss_step_host: loss and gradients of one training step with host buffers, against the oracle."""
+    b, n, m = 2, 900, 640
+    x, y = make_clouds("clustered", b, n, m, seed=5)
+    hx, hy = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+    loss, g1, g2 = pkg.chamfer_loss_step_host(hx, hy, want_grads=True)
+    d1, d2, i1, i2 = oracle.chamfer_forward(x, y, nthreads=8)
+    want = d1.astype(np.float64).mean() + d2.astype(np.float64).mean()
+    assert abs(loss - want) <= 1e-5 * abs(want)
+    gd1 = np.full((b, n), np.float32(1.0) / np.float32(b * n), np.float32)
+    gd2 = np.full((b, m), np.float32(1.0) / np.float32(b * m), np.float32)
+    w1, w2 = oracle.chamfer_backward(x, y, gd1, gd2, i1, i2)
+    for got, ref in ((g1.numpy(), w1), (g2.numpy(), w2)):
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert isinstance(pkg.chamfer_loss_step_host(hx, hy), float)
+
+
 def test_backward_raw_accumulates_into_given_buffers(pkg, oracle, cuda):
     """chamfer_3D.backward adds onto the caller's buffers (the reference relies on caller-zeroed grads)."""
     x, y = make_clouds("uniform", 2, 256, 300, seed=21)

@@ -15,6 +15,8 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
 cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m, float *out, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
 int psd_set_nn_variant(int v);
+cudaError_t psd_launch_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode,
+                                     float *out_min, float *out_inv, cudaStream_t stream);
 void psd_set_tc_debug(float *dbg, int ld);
 void psd_set_tc_prof(long long *prof);
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
@@ -136,6 +138,13 @@ int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *
     return finish("psd_chamfer_mean_loss_backward",
                   psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, nullptr, nullptr, idx1, idx2, b, n, m,
                                               (cudaStream_t)stream, upstream));
+}
+
+int psd_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode, float *min_dist,
+                      float *min_dist_inv, void *stream) {
+    if (mode != 0 && mode != 1) { psd_set_error_msg("psd_proj_min_dist: mode must be 0 (as written) or 1 (intended)"); return -1; }
+    if ((size_t)h * w * 8 > 200 * 1024) { psd_set_error_msg("psd_proj_min_dist: grid too large for the shared-memory table (h*w <= 25600)"); return -1; }
+    return finish("psd_proj_min_dist", psd_launch_proj_min_dist(pred, gt, table, b, h, w, mode, min_dist, min_dist_inv, (cudaStream_t)stream));
 }
 
 int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }

@@ -116,6 +116,17 @@ int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *
                                    const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * psd_proj_min_dist  =  the min-distance branch of get_loss_proj, loss/proj_loss.py:21-40 (with grid_dist, :46-54).
+ * pred, gt: [B,H,W] fp32 projection images (device); table: [H,W] fp32 with table[dh*W+dw] = float32(sqrt(dh^2+dw^2)) + k,
+ * k = how often the caller's `dist_mat += 1` has run (1 in finetune.py:154-158).  Outputs min_dist, min_dist_inv [B,H,W].
+ * mode 0 = as written (weights broadcast along the first pixel pair: the minimum over (h',w') collapses to an end point of
+ * the distance range; bit-exact with the reference's dense evaluation), mode 1 = intended CAPNet-style masked nearest
+ * pixel search (weights on the target pixel).  Returns 1 ok / 0 CUDA error / -1 argument error.
+ * ------------------------------------------------------------------------------------------- */
+int psd_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode, float *min_dist,
+                      float *min_dist_inv, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
  * stages them through its own device workspace on `stream` and copies the results back).
  * ------------------------------------------------------------------------------------------- */

@@ -315,3 +315,33 @@ def torch_fscore(X, Y, threshold=0.0001):
     f = 2 * p1 * p2 / (p1 + p2)
     f[torch.isnan(f)] = 0
     return torch.mean(f), torch.mean(p1), torch.mean(p2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# projection-loss min-distance terms (loss/proj_loss.py:21-40, grid_dist :46-54): dense numpy restatement in fp32
+# ---------------------------------------------------------------------------------------------------------------------
+def grid_dist(grid_h, grid_w):
+    """proj_loss.py:46-54: cdist between all grid points, float64, [H,W,H,W]."""
+    hh = np.arange(grid_h, dtype=np.float64)
+    ww = np.arange(grid_w, dtype=np.float64)
+    dh = hh[:, None, None, None] - hh[None, None, :, None]
+    dw = ww[None, :, None, None] - ww[None, None, None, :]
+    return np.sqrt(dh * dh + dw * dw)
+
+
+def proj_min_dist(pred, gt, dist_mat, mode="as_written"):
+    """min_dist, min_dist_inv for pred, gt [B,H,W] fp32 and dist_mat [H,W,H,W] fp32 (already incremented).
+    as_written: proj_loss.py:25-41 literally (weights broadcast along the FIRST pixel pair);
+    intended:   weights on the target pixel (h',w').  Products in fp32, left to right, like torch."""
+    pred = np.ascontiguousarray(pred, np.float32); gt = np.ascontiguousarray(gt, np.float32)
+    d = np.ascontiguousarray(dist_mat, np.float32)
+    one, big = np.float32(1.0), np.float32(1e6)
+    gt_th = (gt + ((one - gt) * big) * one).astype(np.float32)
+    pred_mask = (pred + ((one - pred) * big) * one).astype(np.float32)
+    if mode == "as_written":
+        a = ((gt_th[:, :, :, None, None] * d[None]).astype(np.float32) * pred[:, :, :, None, None]).astype(np.float32)
+        c = ((gt[:, :, :, None, None] * d[None]).astype(np.float32) * pred_mask[:, :, :, None, None]).astype(np.float32)
+    else:
+        a = ((gt_th[:, None, None, :, :] * d[None]).astype(np.float32) * pred[:, :, :, None, None]).astype(np.float32)
+        c = ((pred_mask[:, None, None, :, :] * d[None]).astype(np.float32) * gt[:, :, :, None, None]).astype(np.float32)
+    return a.min(axis=(3, 4)), c.min(axis=(3, 4))      # np.min propagates NaN like torch.min

@@ -142,10 +142,16 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         if (tid < S) *cluster.map_shared_rank(ucount + rank, tid) = u;
 
         // ---- 2./3. Bid (emd_cuda.cu:95-179): G bidders at a time, tpb threads per bidder
-        int G = 1;
-        while (G < u && G < kEmdThreads) G <<= 1;
-        const int tpb = kEmdThreads / G;
-        for (int a0 = 0; a0 < u; a0 += G) {
+        // The u bidders are processed in passes of G = a power of two bidders (tpb = 1024 / G threads each).  One pass of
+        // the next power of two >= u wastes up to half of the lanes and makes a CTA with u just above a power of two
+        // twice as slow as its cluster mates (they all wait at the cluster barrier): take that pass only if at least
+        // 3/4 of its groups are real, else a full pass of half the size and continue with the remainder.
+        for (int a0 = 0, G = 1; a0 < u; a0 += G) {
+            const int rem = u - a0;
+            G = 1;
+            while (G < rem && G < kEmdThreads) G <<= 1;
+            if (G > 1 && rem * 4 < G * 3) G >>= 1;
+            const int tpb = kEmdThreads / G;
             const int g = tid / tpb, t = tid - g * tpb;
             const int a = a0 + g;
             const bool valid = a < u;
@@ -154,24 +160,57 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
             Top2 r;
             r.best = kNegInit; r.better = kNegInit; r.idx = -1;
-            float R2 = 3.0e38f;
-            if (valid) {
-                for (int k = t; k < n; k += tpb) {
-                    const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-                    if (s <= R2) {
-                        const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
-                        if (v > r.best) {
-                            r.better = r.best; r.best = v; r.idx = k;
-                        } else if (v > r.better) {
-                            r.better = v;
-                        }
-                        const float R = (3.0f - r.better) + 2e-6f;
-                        R2 = R * R * 1.000001f;
+            // Scan with deferred value evaluation.  A pair can change the top two only if v > better, i.e.
+            // sqrt(s) < 3 - better - price <= 3 - better (prices are >= 0): pairs with s above R2 = (3 - better + 2e-6)^2, or
+            // above (3 - better - price[k] + slack)^2 once the object's price is looked at, are skipped exactly.  The survivors' values (IEEE sqrt + fp64 arithmetic, ~30 instructions) used to be evaluated
+            // inside the scan, where one surviving lane sends the whole warp down the long path (27-60 % of the iterations).
+            // Now a lane queues its survivors (in index order, so the strict '>' tie rule is unchanged) and the warp
+            // evaluates them together when some lane has two; `better` for the radius is then the second best of the whole
+            // bidder group inside the warp (a valid lower bound of the final second best), not only the lane's own.
+            const int wl = tpb < 32 ? tpb : 32;
+            float R2 = 3.0e38f, Rg = 3.0e38f;   // squared / plain pruning radius from the group's second best so far
+            int qn = 0, qk0 = 0, qk1 = 0;
+            float qs0 = 0.f, qs1 = 0.f;
+            auto evaluate = [&](int k, float s) {
+                const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
+                if (v > r.best) {
+                    r.better = r.best; r.best = v; r.idx = k;
+                } else if (v > r.better) {
+                    r.better = v;
+                }
+            };
+            auto flush = [&]() {   // warp-uniform
+                if (qn > 0) evaluate(qk0, qs0);
+                if (qn > 1) evaluate(qk1, qs1);
+                qn = 0;
+                float gb = r.best, g2 = r.better;   // group-wide (best, second best with multiplicity) so far
+                for (int o = wl >> 1; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, gb, o);
+                    const float o2 = __shfl_xor_sync(0xffffffffu, g2, o);
+                    g2 = fmaxf(fminf(gb, ob), fmaxf(g2, o2));
+                    gb = fmaxf(gb, ob);
+                }
+                Rg = 3.0f - g2;
+                const float R = Rg + 2e-6f;
+                R2 = R * R * 1.000001f;
+            };
+            // n is a multiple of 1024 and tpb a power of two <= 1024: every lane of the warp runs n / tpb iterations
+            for (int k = t; k < n; k += tpb) {
+                const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+                if (valid && s <= R2) {
+                    // per-object test with the object's own price: v > better needs sqrt(s) < 3 - better - price[k].  The
+                    // slack covers the fp32 rounding of this test and of the reference's value (|terms| are O(1): 3 ulp(4)).
+                    const float pk = price[k];
+                    const float Rk = (Rg - pk) + (4e-6f + 1e-6f * (fabsf(Rg) + fabsf(pk)));
+                    if (Rk > 0.f && s <= Rk * Rk * 1.000002f) {
+                        if (qn == 0) { qk0 = k; qs0 = s; } else { qk1 = k; qs1 = s; }
+                        ++qn;
                     }
                 }
+                if (__any_sync(0xffffffffu, qn == 2)) flush();
             }
+            flush();
             // merge inside the warp over min(tpb,32) lanes
-            const int wl = tpb < 32 ? tpb : 32;
             for (int o = wl >> 1; o > 0; o >>= 1) {
                 const float ob = __shfl_xor_sync(0xffffffffu, r.best, o);
                 const float o2 = __shfl_xor_sync(0xffffffffu, r.better, o);

@@ -173,38 +173,63 @@ struct Frame {        // filter frame of one unit (identical in every helper thr
     int bad, bsel;                // non-finite target seen; B / raw-target buffer
 };
 
-// Exact full scan for the queries on the deferred list, one warp per query; raw targets come from shared memory when
-// the query's cloud/direction is still resident in sraw, else from global memory.  Reference semantics incl. NaN:
-// within a 512-target tile the first element is taken unconditionally and NaN never replaces or is replaced
-// (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
-__device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, const int *fb_list, int nfb, int wi, int nw,
-                                              int lane, const float *sraw, const int *s_rawgroup) {
-    for (int fi = wi; fi < nfb; fi += nw) {
-        const int e = fb_list[fi];
-        const bool ebad = (e >> 30) & 1;
-        const Unit u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
-        const NNDirection &D = p.dir[u.d];
-        const int nt = D.nt;
-        const int j = D.q_begin + u.qblock * kQB + (e & 0xff);
-        const float *__restrict__ qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
-        const float x1 = __ldg(qp), y1 = __ldg(qp + D.q_cs), z1 = __ldg(qp + 2 * D.q_cs);
-        const bool nan_possible = ebad || !(fabsf(x1) < 1e18f) || !(fabsf(y1) < 1e18f) || !(fabsf(z1) < 1e18f);
-        const int grp = group_of(u);
-        const int res = s_rawgroup[0] == grp ? 0 : (s_rawgroup[1] == grp ? 1 : -1);
-        // generic view of the targets: component base pointers and point stride
-        const float *bx, *by, *bz;
-        long long ps;
-        if (res >= 0) { bx = sraw + (res * 3) * kMaxT; by = bx + kMaxT; bz = by + kMaxT; ps = 1; }
-        else { bx = D.t + (long long)u.cloud * D.t_bs; by = bx + D.t_cs; bz = by + D.t_cs; ps = D.t_ps; }
-        unsigned long long key = ~0ull;
-        for (int kb = lane; kb < nt; kb += 8 * 32) {
+// Exact full scan for a query on the deferred list.  fallback_scan: one warp scans part `part` of `nsplit` of the targets
+// and returns the packed (distance, index) minimum (identical in every lane); raw targets come from shared memory when the
+// query's cloud/direction is still resident in sraw, else from global memory.  fallback_write: one thread stores the
+// result.  Reference semantics incl. NaN: within a 512-target tile the first element is taken unconditionally and NaN
+// never replaces or is replaced (chamfer3D.cu:36); a tile result replaces the running result only if strictly smaller (:126).
+struct FbQuery {
+    Unit u;
+    int j, nt, res;
+    float x1, y1, z1;
+    bool nan_possible;
+    const float *bx, *by, *bz;   // generic view of the targets: component base pointers and point stride
+    long long ps;
+};
+__device__ __forceinline__ FbQuery fallback_query(const NNParams &p, int blk_begin, int e, const float *sraw, const int *s_rawgroup) {
+    FbQuery q;
+    q.u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
+    const NNDirection &D = p.dir[q.u.d];
+    q.nt = D.nt;
+    q.j = D.q_begin + q.u.qblock * kQB + (e & 0xff);
+    const float *__restrict__ qp = D.q + (long long)q.u.cloud * D.q_bs + q.j * D.q_ps;
+    q.x1 = __ldg(qp); q.y1 = __ldg(qp + D.q_cs); q.z1 = __ldg(qp + 2 * D.q_cs);
+    q.nan_possible = ((e >> 30) & 1) || !(fabsf(q.x1) < 1e18f) || !(fabsf(q.y1) < 1e18f) || !(fabsf(q.z1) < 1e18f);
+    const int grp = group_of(q.u);
+    q.res = s_rawgroup[0] == grp ? 0 : (s_rawgroup[1] == grp ? 1 : -1);
+    if (q.res >= 0) { q.bx = sraw + (q.res * 3) * kMaxT; q.by = q.bx + kMaxT; q.bz = q.by + kMaxT; q.ps = 1; }
+    else { q.bx = D.t + (long long)q.u.cloud * D.t_bs; q.by = q.bx + D.t_cs; q.bz = q.by + D.t_cs; q.ps = D.t_ps; }
+    return q;
+}
+__device__ __forceinline__ unsigned long long fallback_scan(const FbQuery &q, int part, int nsplit, int lane) {
+    const float x1 = q.x1, y1 = q.y1, z1 = q.z1;
+    const int nt = q.nt;
+    unsigned long long key = ~0ull;
+    if (q.res >= 0 && !q.nan_possible) {
+        // resident cloud, finite data: 4 targets per lane and step straight from the SoA copy (3 x LDS.128), running
+        // (distance, index) minimum in index order with strict '<' -- no NaN can occur
+        float dbest = 3.0e38f;
+        int ibest = 0x7fffffff;
+        for (int k0 = 4 * lane + 128 * part; k0 < nt; k0 += 128 * nsplit) {
+            const float4 xa = *reinterpret_cast<const float4 *>(q.bx + k0), ya = *reinterpret_cast<const float4 *>(q.by + k0),
+                         za = *reinterpret_cast<const float4 *>(q.bz + k0);
+            const float d0 = sqdist_exact(xa.x - x1, ya.x - y1, za.x - z1), d1 = sqdist_exact(xa.y - x1, ya.y - y1, za.y - z1);
+            const float d2 = sqdist_exact(xa.z - x1, ya.z - y1, za.z - z1), d3 = sqdist_exact(xa.w - x1, ya.w - y1, za.w - z1);
+            if (d0 < dbest) { dbest = d0; ibest = k0; }
+            if (k0 + 1 < nt && d1 < dbest) { dbest = d1; ibest = k0 + 1; }
+            if (k0 + 2 < nt && d2 < dbest) { dbest = d2; ibest = k0 + 2; }
+            if (k0 + 3 < nt && d3 < dbest) { dbest = d3; ibest = k0 + 3; }
+        }
+        if (ibest != 0x7fffffff) key = pack_key(dbest, ibest);
+    } else {
+        for (int kb = lane + 256 * part; kb < nt; kb += 256 * nsplit) {
             float dd[8], dts[8];
 #pragma unroll
             for (int q8 = 0; q8 < 8; ++q8) {
                 const long long k = min(kb + q8 * 32, nt - 1);
-                dd[q8] = sqdist_exact(bx[k * ps] - x1, by[k * ps] - y1, bz[k * ps] - z1);
+                dd[q8] = sqdist_exact(q.bx[k * q.ps] - x1, q.by[k * q.ps] - y1, q.bz[k * q.ps] - z1);
                 const long long kt = k & ~(long long)(kRefTile - 1);
-                dts[q8] = nan_possible ? sqdist_exact(bx[kt * ps] - x1, by[kt * ps] - y1, bz[kt * ps] - z1) : 0.f;
+                dts[q8] = q.nan_possible ? sqdist_exact(q.bx[kt * q.ps] - x1, q.by[kt * q.ps] - y1, q.bz[kt * q.ps] - z1) : 0.f;
             }
 #pragma unroll
             for (int q8 = 0; q8 < 8; ++q8) {
@@ -215,22 +240,33 @@ __device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, 
                 }
             }
         }
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = shfl_xor_u64(key, o);
-            key = other < key ? other : key;
-        }
-        if (lane == 0) {
-            const float d0 = sqdist_exact(bx[0] - x1, by[0] - y1, bz[0] - z1);
-            float dres;
-            int ires;
-            if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
-            else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
-            D.dist[(long long)u.cloud * D.nq + j] = dres;
-            D.idx[(long long)u.cloud * D.nq + j] = ires;
-            if (p.sums) atomicAdd(p.sums + u.cloud * 2 + D.slot, dres);
-            if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + u.cloud * 2 + D.slot, 1);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = shfl_xor_u64(key, o);
+        key = other < key ? other : key;
+    }
+    return key;
+}
+__device__ __forceinline__ void fallback_write(const NNParams &p, const FbQuery &q, unsigned long long key) {
+    const NNDirection &D = p.dir[q.u.d];
+    const float d0 = sqdist_exact(q.bx[0] - q.x1, q.by[0] - q.y1, q.bz[0] - q.z1);
+    float dres;
+    int ires;
+    if (d0 != d0) { dres = d0; ires = 0; }   // tile 0 poisoned: stays NaN, index 0
+    else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
+    D.dist[(long long)q.u.cloud * D.nq + q.j] = dres;
+    D.idx[(long long)q.u.cloud * D.nq + q.j] = ires;
+    if (p.sums) atomicAdd(p.sums + q.u.cloud * 2 + D.slot, dres);
+    if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + q.u.cloud * 2 + D.slot, 1);
+}
+// one warp per query (used by the helpers when the list has to be flushed in the middle of the kernel)
+__device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, const int *fb_list, int nfb, int wi, int nw,
+                                              int lane, const float *sraw, const int *s_rawgroup) {
+    for (int fi = wi; fi < nfb; fi += nw) {
+        const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+        const unsigned long long key = fallback_scan(q, 0, 1, lane);
+        if (lane == 0) fallback_write(p, q, key);
     }
 }
 
@@ -692,14 +728,29 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         if (DBG && pf && ht == 0) pf[60] = a60;
     }
 
-    // ---------------- the deferred exact scans of this CTA, one warp per query, by every warp (measured faster than a
-    // CTA-wide scan per query: 41.5 vs 43.4 us at B=32, N=M=2048)
+    // ---------------- the deferred exact scans of this CTA, by every warp: with few queries (the usual 0-3) each query is
+    // split over up to four warps whose partial minima meet in a shared-memory atomicMin
     tc_fence_before();
     __syncthreads();
     if (tid == 0) stamp(3);
     {
         const int nfb = *s_nfb;
-        run_fallbacks(p, blk_begin, fb_list, nfb, warp, kThreadsTC / 32, lane, sraw, s_rawgroup);
+        constexpr int kW = kThreadsTC / 32;
+        const int nsplit = nfb * 4 <= kW ? 4 : (nfb * 2 <= kW ? 2 : 1);
+        unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(part);   // partial results are dead by now
+        for (int i = tid; i < nfb; i += kThreadsTC) s_keys[i] = ~0ull;
+        __syncthreads();
+        for (int item = warp; item < nfb * nsplit; item += kW) {
+            const int fi = item / nsplit;
+            const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+            const unsigned long long key = fallback_scan(q, item - fi * nsplit, nsplit, lane);
+            if (lane == 0) atomicMin(s_keys + fi, key);
+        }
+        __syncthreads();
+        for (int fi = tid; fi < nfb; fi += kThreadsTC) {
+            const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+            fallback_write(p, q, s_keys[fi]);
+        }
         if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
     }
     if (tid == 0) stamp(4);

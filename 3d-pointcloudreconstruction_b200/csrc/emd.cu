@@ -195,9 +195,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 R2 = R * R * 1.000001f;
             };
             // n is a multiple of 1024 and tpb a power of two <= 1024: every lane of the warp runs n / tpb iterations
-            for (int k = t; k < n; k += tpb) {
-                const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-                if (valid && s <= R2) {
+            auto consider = [&](int k, float s, bool pass) {   // warp-uniform call; `pass` = survived the price-free test
+                if (pass) {
                     // per-object test with the object's own price: v > better needs sqrt(s) < 3 - better - price[k].  The
                     // slack covers the fp32 rounding of this test and of the reference's value (|terms| are O(1): 3 ulp(4)).
                     const float pk = price[k];
@@ -208,6 +207,28 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                     }
                 }
                 if (__any_sync(0xffffffffu, qn == 2)) flush();
+            };
+            if (((n / tpb) & 3) == 0) {
+                // four objects per lane and step: 12 shared-memory loads in flight, one vote for the common all-skipped case
+                const int st = tpb;
+                for (int k = t; k < n; k += 4 * st) {
+                    const float s0 = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+                    const float s1 = sqdist_exact(ox[k + st] - x1, oy[k + st] - y1, oz[k + st] - z1);
+                    const float s2 = sqdist_exact(ox[k + 2 * st] - x1, oy[k + 2 * st] - y1, oz[k + 2 * st] - z1);
+                    const float s3 = sqdist_exact(ox[k + 3 * st] - x1, oy[k + 3 * st] - y1, oz[k + 3 * st] - z1);
+                    const bool p0 = valid && s0 <= R2, p1 = valid && s1 <= R2, p2 = valid && s2 <= R2, p3 = valid && s3 <= R2;
+                    if (__any_sync(0xffffffffu, p0 || p1 || p2 || p3)) {
+                        consider(k, s0, p0);
+                        consider(k + st, s1, p1);
+                        consider(k + 2 * st, s2, p2);
+                        consider(k + 3 * st, s3, p3);
+                    }
+                }
+            } else {
+                for (int k = t; k < n; k += tpb) {
+                    const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+                    consider(k, s, valid && s <= R2);
+                }
             }
             flush();
             // merge inside the warp over min(tpb,32) lanes

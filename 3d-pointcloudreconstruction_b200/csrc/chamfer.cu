@@ -548,7 +548,7 @@ static float *g_tc_dbg = nullptr;   // one-shot debug dump target of the tensor-
 static int g_tc_dbg_ld = 0;
 
 bool psd_nn_tc_supported(const NNParams &p);                                               // chamfer_nn_tc.cu
-cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof);
+cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b);
 static long long *g_tc_prof = nullptr;
 void psd_set_tc_prof(long long *prof) { g_tc_prof = prof; }
 cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int *error, int reset);
@@ -587,6 +587,7 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
         if (qb0 + qc > nq) qc = nq - qb0;
         D.q_begin = qb0; D.q_count = qc;
         D.qblocks = (qc + QB - 1) / QB;
+        D.ntt = 1; D.ws = nullptr;
     };
     fill(p.dir[0], xyz1, n, xyz2, m, dist1, idx1, 0);
     fill(p.dir[1], xyz2, m, xyz1, n, dist2, idx2, 1);
@@ -603,7 +604,7 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     if ((g_nn_variant == 3 || (g_nn_variant == 0 && blocks >= 2LL * g_num_sms)) && psd_nn_tc_supported(p)) {
         float *dbg = g_tc_dbg;
         g_tc_dbg = nullptr;
-        return psd_launch_nn_tc(p, g_num_sms, stream, dbg, g_tc_dbg_ld, g_tc_prof);
+        return psd_launch_nn_tc(p, g_num_sms, stream, dbg, g_tc_dbg_ld, g_tc_prof, b);
     }
     // Launches that give every 4-warp group of every SM at least two blocks run the grouped kernel (resolve and
     // tile staging overlap the filter); smaller launches keep all 16 warps of a CTA on one block (latency).

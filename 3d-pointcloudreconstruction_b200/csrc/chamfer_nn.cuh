@@ -23,6 +23,11 @@ struct NNDirection {
     int q_begin, q_count;  // query slice handled by this launch
     int qblocks;           // 128-query blocks per cloud for this direction
     int slot;              // 0/1: column in sums[B,2] / fs_count[B,2]
+    // tensor-core kernel only: the targets are cut into ntt tiles of 2048 (a unit = one query block x one tile).  With
+    // ntt > 1 every unit merges its exact (distance, index) into ws[cloud*nq + j] with a 64-bit atomicMin and a
+    // finalize kernel unpacks dist / idx; with ntt == 1 (ws == nullptr) the kernel writes dist / idx itself.
+    int ntt;
+    unsigned long long *ws;
 };
 
 struct NNParams {

@@ -156,17 +156,44 @@ __device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
 
 struct Unit {
     int d, cloud, qblock;
+    int ttile, t0, nt;     // target tile of the unit: index, first target, number of targets (<= kMaxT)
 };
+// unit order inside a direction: cloud, target tile, query block -- consecutive units of a CTA share a B operand
 __device__ __forceinline__ Unit decode_unit(const NNParams &p, int blk) {
     Unit u;
     u.d = blk >= p.blocks_dir0 ? 1 : 0;
+    const NNDirection &D = p.dir[u.d];
     const int bid = u.d ? blk - p.blocks_dir0 : blk;
-    const int qbn = p.dir[u.d].qblocks;
-    u.cloud = bid / qbn;
-    u.qblock = bid - u.cloud * qbn;
+    const int per_cloud = D.qblocks * D.ntt;
+    u.cloud = bid / per_cloud;
+    const int rem = bid - u.cloud * per_cloud;
+    u.ttile = D.ntt == 1 ? 0 : rem / D.qblocks;   // (single-tile launches: one division less per decode)
+    u.qblock = rem - u.ttile * D.qblocks;
+    u.t0 = u.ttile * kMaxT;
+    u.nt = min(kMaxT, D.nt - u.t0);
     return u;
 }
-__device__ __forceinline__ int group_of(const Unit &u) { return u.d * 0x40000000 + u.cloud; }
+// unit blk -> unit blk + 1 without the integer divisions of decode_unit (they cost the single MMA thread ~500 cycles per unit)
+__device__ __forceinline__ void advance_unit(const NNParams &p, Unit &u, int blk_next) {
+    if (blk_next == p.blocks_dir0) { u = decode_unit(p, blk_next); return; }   // direction switch
+    const NNDirection &D = p.dir[u.d];
+    if (++u.qblock == D.qblocks) {
+        u.qblock = 0;
+        if (++u.ttile == D.ntt) { u.ttile = 0; ++u.cloud; }
+        u.t0 = u.ttile * kMaxT;
+        u.nt = min(kMaxT, D.nt - u.t0);
+    }
+}
+__device__ __forceinline__ int group_of(const NNParams &p, const Unit &u) { return u.d * 0x40000000 + u.cloud * p.dir[u.d].ntt + u.ttile; }
+__device__ __forceinline__ const float *targets_of(const NNParams &p, const Unit &u) {
+    const NNDirection &D = p.dir[u.d];
+    return D.t + (long long)u.cloud * D.t_bs + (long long)u.t0 * D.t_ps;
+}
+// store one query's exact result: directly, or merged over the target tiles through the 64-bit workspace
+__device__ __forceinline__ void store_result(const NNDirection &D, const Unit &u, int j, float dist, int idx_local) {
+    if (D.ws) atomicMin(D.ws + (long long)u.cloud * D.nq + j, pack_key(dist, u.t0 + idx_local));
+    else { D.dist[(long long)u.cloud * D.nq + j] = dist; D.idx[(long long)u.cloud * D.nq + j] = u.t0 + idx_local; }
+}
 
 struct Frame {        // filter frame of one unit (identical in every helper thread)
     float cx, cy, cz, cs, wmax;   // centre, power-of-two scale, max |t'|^2
@@ -190,15 +217,15 @@ __device__ __forceinline__ FbQuery fallback_query(const NNParams &p, int blk_beg
     FbQuery q;
     q.u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
     const NNDirection &D = p.dir[q.u.d];
-    q.nt = D.nt;
+    q.nt = q.u.nt;
     q.j = D.q_begin + q.u.qblock * kQB + (e & 0xff);
     const float *__restrict__ qp = D.q + (long long)q.u.cloud * D.q_bs + q.j * D.q_ps;
     q.x1 = __ldg(qp); q.y1 = __ldg(qp + D.q_cs); q.z1 = __ldg(qp + 2 * D.q_cs);
     q.nan_possible = ((e >> 30) & 1) || !(fabsf(q.x1) < 1e18f) || !(fabsf(q.y1) < 1e18f) || !(fabsf(q.z1) < 1e18f);
-    const int grp = group_of(q.u);
+    const int grp = group_of(p, q.u);
     q.res = s_rawgroup[0] == grp ? 0 : (s_rawgroup[1] == grp ? 1 : -1);
     if (q.res >= 0) { q.bx = sraw + (q.res * 3) * kMaxT; q.by = q.bx + kMaxT; q.bz = q.by + kMaxT; q.ps = 1; }
-    else { q.bx = D.t + (long long)q.u.cloud * D.t_bs; q.by = q.bx + D.t_cs; q.bz = q.by + D.t_cs; q.ps = D.t_ps; }
+    else { q.bx = targets_of(p, q.u); q.by = q.bx + D.t_cs; q.bz = q.by + D.t_cs; q.ps = D.t_ps; }
     return q;
 }
 __device__ __forceinline__ unsigned long long fallback_scan(const FbQuery &q, int part, int nsplit, int lane) {
@@ -250,6 +277,10 @@ __device__ __forceinline__ unsigned long long fallback_scan(const FbQuery &q, in
 }
 __device__ __forceinline__ void fallback_write(const NNParams &p, const FbQuery &q, unsigned long long key) {
     const NNDirection &D = p.dir[q.u.d];
+    if (D.ws) {   // merged over the target tiles; the finalize kernel applies the tile-0 NaN rule and the epilogues
+        if (key != ~0ull) atomicMin(D.ws + (long long)q.u.cloud * D.nq + q.j, key + (unsigned long long)q.u.t0);
+        return;
+    }
     const float d0 = sqdist_exact(q.bx[0] - q.x1, q.by[0] - q.y1, q.bz[0] - q.z1);
     float dres;
     int ires;
@@ -412,14 +443,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     if (nunits > 0) {
         const Unit u = decode_unit(p, blk_begin);
         const NNDirection &D = p.dir[u.d];
-        group0 = group_of(u);
-        const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
+        group0 = group_of(p, u);
+        const float *__restrict__ tb = targets_of(p, u);
 #pragma unroll
         for (int comp = 0; comp < 3; ++comp)
-            for (int k = tid; k < D.nt; k += kThreadsTC) cp_async4(sraw + comp * kMaxT + k, tb + k * D.t_ps + comp * D.t_cs);
+            for (int k = tid; k < u.nt; k += kThreadsTC) cp_async4(sraw + comp * kMaxT + k, tb + k * D.t_ps + comp * D.t_cs);
         cp_async_wait_all();
         __syncthreads();
-        build_b(D.nt, 0, tid, kThreadsTC, warp, [] { __syncthreads(); }, fr0);
+        build_b(u.nt, 0, tid, kThreadsTC, warp, [] { __syncthreads(); }, fr0);
         fence_async_smem();
         __syncthreads();
         pick_stats(kThreadsTC / 32, fr0);
@@ -434,9 +465,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         const uint32_t tlane = tmem_base + ((uint32_t)(r * 32) << 16);
         int g0 = 0;
         long long a59 = 0;
+        Unit u = decode_unit(p, blk_begin);
         for (int ul = 0; ul < nunits; ++ul) {
-            const Unit u = decode_unit(p, blk_begin + ul);
-            const int ntiles = (p.dir[u.d].nt + kTileN - 1) / kTileN;
+            if (ul > 0) advance_unit(p, u, blk_begin + ul);
+            const int ntiles = (u.nt + kTileN - 1) / kTileN;
             float best = kBig, second = kBig;
             int bchunk = 0;
             auto chunk = [&](const uint32_t (&v)[32], int cid) {
@@ -495,10 +527,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         if (lane == 0) {
             int g = 0, grp = -1, bsel = 1;
             long long a56 = 0, a57 = 0, a61 = 0, a62 = 0;   // DBG: wait / issue cycle totals
+            Unit u = decode_unit(p, blk_begin);
             for (int ul = 0; ul < nunits; ++ul) {
-                const Unit u = decode_unit(p, blk_begin + ul);
-                const int ntiles = (p.dir[u.d].nt + kTileN - 1) / kTileN;
-                if (group_of(u) != grp) { grp = group_of(u); bsel ^= 1; }
+                if (ul > 0) advance_unit(p, u, blk_begin + ul);
+                const int ntiles = (u.nt + kTileN - 1) / kTileN;
+                if (group_of(p, u) != grp) { grp = group_of(p, u); bsel ^= 1; }
                 long long w0 = DBG ? clock64() : 0;
                 mbar_wait(bar_ready + 8 * (ul & 1), (ul >> 1) & 1, s_abort);
                 if (DBG) a56 += clock64() - w0;
@@ -531,11 +564,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         bool need_b = false;
 
         // does staging unit ul replace the B operand?  (uniform)
-        auto stage_changes_group = [&](int ul) { return group_of(decode_unit(p, blk_begin + ul)) != st_group; };
+        auto stage_changes_group = [&](const Unit &u) { return group_of(p, u) != st_group; };
         // stage, part 1: put the global loads of unit ul in flight -- its 128 raw queries into registers and, if its
         // cloud/direction is not the staged one, its raw targets into sraw[other buffer] by cp.async.
-        auto stage_issue = [&](int ul) {
-            const Unit u = decode_unit(p, blk_begin + ul);
+        auto stage_issue = [&](int ul, const Unit &u) {
             const NNDirection &D = p.dir[u.d];
             if (ht < kQB) {
                 int j = D.q_begin + u.qblock * kQB + ht;
@@ -544,13 +576,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 const float *qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
                 pq1 = __ldg(qp); pq2 = __ldg(qp + D.q_cs); pq3 = __ldg(qp + 2 * D.q_cs);
             }
-            const int group = group_of(u);
+            const int group = group_of(p, u);
             need_b = group != st_group;
             if (need_b) {
                 st_group = group;
                 st_bsel ^= 1;
-                const int nt = D.nt;
-                const float *__restrict__ tb = D.t + (long long)u.cloud * D.t_bs;
+                const int nt = u.nt;
+                const float *__restrict__ tb = targets_of(p, u);
                 const long long tps = D.t_ps, tcs = D.t_cs;
                 float *rx = sraw + (st_bsel * 3) * kMaxT;
 #pragma unroll
@@ -559,13 +591,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             }
         };
         // stage, part 2: build the operands of unit ul in shared memory and signal the MMA warp.
-        auto stage_finish = [&](int ul) {
-            const Unit u = decode_unit(p, blk_begin + ul);
+        auto stage_finish = [&](int ul, const Unit &u) {
             const NNDirection &D = p.dir[u.d];
             if (need_b) {
                 cp_async_wait_all();
                 help_bar();   // every helper's raw targets have landed
-                build_b(D.nt, st_bsel, ht, kHelpThreads, hw, [] { help_bar(); }, fr_st);
+                build_b(u.nt, st_bsel, ht, kHelpThreads, hw, [] { help_bar(); }, fr_st);
                 if (ht == 0) s_rawgroup[st_bsel] = st_group;
             }
             if (ht < kQB) {
@@ -591,10 +622,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         //   B  4 lanes per query: exact rescan of the best chunk (32 targets) from the raw targets in shared memory
         //   C  queries that fail the margin test go to the deferred list (exact full scan at the end of the kernel)
         constexpr int kQW = (kQB + kHelpWarps - 1) / kHelpWarps;   // 19
-        auto resolve = [&](int ul, const Frame &fr) {
-            const Unit u = decode_unit(p, blk_begin + ul);
+        auto resolve = [&](int ul, const Unit &u, const Frame &fr) {
             const NNDirection &D = p.dir[u.d];
-            const int nt = D.nt;
+            const int nt = u.nt;
             const float *pp = part + (ul & 1) * 2 * 3 * kQB;
             const float *sqp = sq + (ul % 3) * 3 * kQB;
             const float *rx = sraw + (fr.bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
@@ -668,15 +698,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     if (od < dbest || (od == dbest && oi < ibest)) { dbest = od; ibest = oi; }
                 }
                 if (okq && sub == 0) {
-                    D.dist[(long long)u.cloud * D.nq + jq] = dbest;
-                    D.idx[(long long)u.cloud * D.nq + jq] = ibest;
+                    store_result(D, u, jq, dbest, ibest);
                     ws += dbest;
                     wc += dbest < p.fs_thr ? 1 : 0;
                 }
             }
             // ---- C: the exact full scan of a query that failed the margin test is deferred to the end of the kernel
             if (live && !ok) fb_list[atomicAdd(s_nfb, 1)] = (ul << 8) | ql | (fr.bad ? (1 << 30) : 0);
-            if (p.sums != nullptr || p.fs_count != nullptr) {   // fused epilogues, one atomic per warp
+            if ((p.sums != nullptr || p.fs_count != nullptr) && D.ws == nullptr) {   // fused epilogues, one atomic per warp
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     ws += __shfl_xor_sync(0xffffffffu, ws, o);
@@ -690,8 +719,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         };
 
         Frame f0 = fr_st, f1 = fr_st;     // frames of unit ul and ul + 1
-        if (nunits > 0) { stage_issue(0); stage_finish(0); f0 = fr_st; }
-        if (nunits > 1) { stage_issue(1); stage_finish(1); f1 = fr_st; }
+        Unit u0 = decode_unit(p, blk_begin), u1 = u0, u2 = u0;   // units ul, ul + 1, ul + 2 (advanced without divisions)
+        if (nunits > 0) { stage_issue(0, u0); stage_finish(0, u0); f0 = fr_st; }
+        if (nunits > 1) { advance_unit(p, u1, blk_begin + 1); stage_issue(1, u1); stage_finish(1, u1); f1 = fr_st; }
+        u2 = u1;
         if (ht == 0) stamp(2);
         long long a60 = 0;
         for (int ul = 0; ul < nunits; ++ul) {
@@ -699,12 +730,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             // their buffer is not the one resolve(ul) still reads: units ul and ul+1 of the same cloud/direction.
             const bool stage_next = ul + 2 < nunits;
             bool issued = false;
-            if (stage_next && (!stage_changes_group(ul + 2) || f0.bsel == f1.bsel)) { stage_issue(ul + 2); issued = true; }
+            if (stage_next) {
+                advance_unit(p, u2, blk_begin + ul + 2);
+                if (!stage_changes_group(u2) || f0.bsel == f1.bsel) { stage_issue(ul + 2, u2); issued = true; }
+            }
             const long long w0 = DBG ? clock64() : 0;
             mbar_wait(bar_part + 8 * (ul & 1), (ul >> 1) & 1, s_abort);   // scanners parked unit ul; its MMAs are complete
             if (DBG) a60 += clock64() - w0;
             if (ht == 0) stamp(9 + ul * 6);
-            resolve(ul, f0);
+            resolve(ul, u0, f0);
             if (ht == 0) stamp(10 + ul * 6);
             help_bar();   // every helper is done with part/sq/sraw of unit ul before anything is restaged
             {   // deferred exact scans: flush when the next unit could overflow the list
@@ -719,10 +753,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             }
             f0 = f1;
             if (stage_next) {
-                if (!issued) stage_issue(ul + 2);
-                stage_finish(ul + 2);
+                if (!issued) stage_issue(ul + 2, u2);
+                stage_finish(ul + 2, u2);
                 f1 = fr_st;
             }
+            u0 = u1; u1 = u2;
             if (ht == 0) stamp(11 + ul * 6);
         }
         if (DBG && pf && ht == 0) pf[60] = a60;
@@ -763,12 +798,62 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 
 using namespace psd;
 
-// Shapes the tensor-core kernel takes: both target clouds fit the resident B operand.
+// Finalize kernel of the multi-tile mode: unpack the merged (distance, index) keys, apply the reference's tile-0 NaN rule
+// (a NaN distance to target 0 poisons the result: chamfer3D.cu:36,126) and the fused loss-sum / F-score epilogue.
+namespace psd {
+namespace tc {
+__global__ void __launch_bounds__(256) chamfer_nn_tc_finalize_kernel(const NNParams p, int b) {
+    const long long n0 = p.dir[0].ws ? (long long)b * p.dir[0].q_count : 0;
+    const long long n1 = p.dir[1].ws ? (long long)b * p.dir[1].q_count : 0;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gid < n0 + n1;
+    const int d = (active && gid >= n0) ? 1 : 0;
+    const NNDirection &D = p.dir[d];
+    float dres = 0.f;
+    int cloud = -1;
+    if (active) {
+        const long long e = d ? gid - n0 : gid;
+        cloud = (int)(e / D.q_count);
+        const int j = D.q_begin + (int)(e - (long long)cloud * D.q_count);
+        const unsigned long long key = D.ws[(long long)cloud * D.nq + j];
+        const float *qp = D.q + (long long)cloud * D.q_bs + (long long)j * D.q_ps;
+        const float d0 = exact_d(D.t + (long long)cloud * D.t_bs, D.t_ps, D.t_cs, 0, __ldg(qp), __ldg(qp + D.q_cs), __ldg(qp + 2 * D.q_cs));
+        int ires;
+        if (d0 != d0) { dres = d0; ires = 0; }
+        else { dres = __uint_as_float((unsigned int)(key >> 32)); ires = (int)(key & 0xffffffffu); }
+        D.dist[(long long)cloud * D.nq + j] = dres;
+        D.idx[(long long)cloud * D.nq + j] = ires;
+    }
+    if (p.sums != nullptr || p.fs_count != nullptr) {
+        // warp-aggregated when the whole warp sits in one cloud/direction, else one atomic per thread
+        const int key2 = active ? cloud * 2 + D.slot : -1;
+        const int k0 = __shfl_sync(0xffffffffu, key2, 0);
+        const bool uniform = __all_sync(0xffffffffu, key2 == k0);
+        float ws = active ? dres : 0.f;
+        int wc = (active && dres < p.fs_thr) ? 1 : 0;
+        if (uniform) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ws += __shfl_xor_sync(0xffffffffu, ws, o); wc += __shfl_xor_sync(0xffffffffu, wc, o); }
+            if ((threadIdx.x & 31) == 0 && k0 >= 0) {
+                if (p.sums) atomicAdd(p.sums + k0, ws);
+                if (p.fs_count && wc) atomicAdd(p.fs_count + k0, wc);
+            }
+        } else if (active) {
+            if (p.sums) atomicAdd(p.sums + key2, ws);
+            if (p.fs_count && wc) atomicAdd(p.fs_count + key2, wc);
+        }
+    }
+}
+}  // namespace tc
+}  // namespace psd
+
+// The tensor-core kernel takes every shape: target clouds of more than 2048 points are cut into tiles (multi-tile mode).
 bool psd_nn_tc_supported(const NNParams &p) {
-    return p.dir[0].nt <= tc::kMaxT && p.dir[1].nt <= tc::kMaxT;
+    const long long t0 = (p.dir[0].nt + tc::kMaxT - 1) / tc::kMaxT, t1 = (p.dir[1].nt + tc::kMaxT - 1) / tc::kMaxT;
+    return (long long)p.blocks_dir0 * t0 + (long long)(p.total_blocks - p.blocks_dir0) * t1 < 0x3fffffffLL;
 }
 
-cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof) {
+cudaError_t psd_launch_nn_tc(const NNParams &p_in, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc::chamfer_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTC);
@@ -776,10 +861,44 @@ cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    NNParams p = p_in;
+    // target tiles; directions with more than one tile merge through a stream-ordered 64-bit workspace [B, nq]
+    unsigned long long *ws = nullptr;
+    size_t ws_elems = 0;
+    for (int d = 0; d < 2; ++d) {
+        p.dir[d].ntt = (p.dir[d].nt + tc::kMaxT - 1) / tc::kMaxT;
+        if (p.dir[d].ntt > 1) ws_elems += (size_t)b * p.dir[d].nq;
+    }
+    if (ws_elems) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_elems * sizeof(unsigned long long), stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ws, 0xff, ws_elems * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+    }
+    {
+        unsigned long long *w = ws;
+        for (int d = 0; d < 2; ++d) {
+            p.dir[d].ws = p.dir[d].ntt > 1 ? w : nullptr;
+            if (p.dir[d].ntt > 1) w += (size_t)b * p.dir[d].nq;
+        }
+    }
+    const int blocks0 = p.blocks_dir0 * p.dir[0].ntt;
+    const int blocks1 = (p.total_blocks - p.blocks_dir0) * p.dir[1].ntt;
+    p.blocks_dir0 = blocks0;
+    p.total_blocks = blocks0 + blocks1;
     const int grid = p.total_blocks < num_sms ? p.total_blocks : num_sms;
     if (dbg || prof) tc::chamfer_nn_tc_kernel<true><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, dbg, dbg_ld, prof);
     else tc::chamfer_nn_tc_kernel<false><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, nullptr, 0, nullptr);
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (ws_elems) {
+        if (e == cudaSuccess) {
+            const long long total = (p.dir[0].ws ? (long long)b * p.dir[0].q_count : 0) + (p.dir[1].ws ? (long long)b * p.dir[1].q_count : 0);
+            tc::chamfer_nn_tc_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, b);
+            e = cudaGetLastError();
+        }
+        const cudaError_t e2 = cudaFreeAsync(ws, stream);
+        if (e == cudaSuccess) e = e2;
+    }
+    return e;
 }
 
 cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int *error, int reset) {

@@ -35,7 +35,8 @@ def assert_bit_equal(got, want, what):
 
 
 @pytest.mark.parametrize("kind", ["uniform", "clustered", "lattice", "dup", "offset"])
-@pytest.mark.parametrize("shape", [(2, 1024, 1024), (3, 1000, 2000), (1, 1, 1), (2, 7, 513), (2, 515, 3), (1, 129, 1025), (4, 2048, 2048)])
+@pytest.mark.parametrize("shape", [(2, 1024, 1024), (3, 1000, 2000), (1, 1, 1), (2, 7, 513), (2, 515, 3), (1, 129, 1025), (4, 2048, 2048),
+                                   (1, 2500, 4100), (2, 4097, 300), (1, 2049, 6145)])   # > 2048 targets: multi-tile mode of the TC kernel
 def test_forward_bit_exact(pkg, oracle, cuda, kind, shape):
     b, n, m = shape
     x, y = make_clouds(kind, b, n, m, seed=1234 + n + m)
@@ -79,6 +80,20 @@ def test_forward_nan_inf_semantics(pkg, oracle, cuda):
     got = run_forward(pkg, cuda, x, y)
     want = oracle.chamfer_forward(x, y)
     assert_bit_equal(got, want, "nan/inf")
+
+
+def test_forward_nan_semantics_across_target_tiles(pkg, oracle, cuda):
+    """> 2048 targets (multi-tile mode of the tensor-core kernel): NaN at target 0 poisons, NaNs at 512-tile heads in later
+    2048-tiles drop their 512-tile, a NaN elsewhere is ignored."""
+    x, y = make_clouds("uniform", 2, 400, 5000, seed=19)
+    y[0, 0, 2] = np.nan        # target 0 of cloud 0: every query of cloud 0 keeps NaN / index 0
+    y[1, 2048, 0] = np.nan     # head of 512-tile 4 (first element of the second 2048-tile) of cloud 1
+    y[1, 4608, 1] = np.nan     # head of 512-tile 9
+    y[1, 3000, 1] = np.nan     # inside a tile: ignored
+    x[1, 7, 1] = np.nan        # a NaN query
+    got = run_forward(pkg, cuda, x, y)
+    want = oracle.chamfer_forward(x, y)
+    assert_bit_equal(got, want, "nan across tiles")
 
 
 def test_forward_huge_and_tiny_magnitudes(pkg, oracle, cuda):

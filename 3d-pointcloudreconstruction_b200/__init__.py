@@ -14,10 +14,10 @@ from . import proj_loss        # loss/proj_loss.py mirror (get_loss_proj, grid_d
 from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction
 from .emd_module import emdFunction, emdModule
 from .fscore import fscore, chamfer_fscore_fused
-from .loss import Loss, chamfer_loss_step_host
+from .loss import Loss, chamfer_loss_step_host, ChamferLossPipeline
 from .metrics import Metrics
 
 __all__ = [
     "chamfer_3D", "emd", "proj_loss", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
-    "fscore", "chamfer_fscore_fused", "Loss", "chamfer_loss_step_host", "Metrics",
+    "fscore", "chamfer_fscore_fused", "Loss", "chamfer_loss_step_host", "ChamferLossPipeline", "Metrics",
 ]

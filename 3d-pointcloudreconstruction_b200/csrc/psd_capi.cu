@@ -207,24 +207,35 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
 
 // fwd + fused mean loss + bwd of one training step with HOST inputs: the end-to-end form of Loss.get_chamfer_loss
 // (loss/loss.py:30-37) followed by loss.backward().  Gradients stay on the device unless host pointers are given.
-static float *g_ws2 = nullptr;
-static size_t g_ws2_bytes = 0;
+static float *g_ws2[2] = {nullptr, nullptr};
+static size_t g_ws2_bytes[2] = {0, 0};
+int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                                  int slot, int sync, void *stream_);
 int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
                                float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
                                void *stream_) {
+    return psd_chamfer_loss_step_host_ex(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, gradxyz1_dev,
+                                         gradxyz2_dev, 0, 1, stream_);
+}
+int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                                  int slot, int sync, void *stream_) {
+    if (slot != 0 && slot != 1) { psd_set_error_msg("psd_chamfer_loss_step_host_ex: slot must be 0 or 1"); return -1; }
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
     // layout: xyz1 | xyz2 | grad1 | grad2 | dist1 | dist2 | idx1 | idx2 | sums[2b] | loss
     const size_t nfloat = 6 * (s1 + s2) + 2 * (s1 + s2) + 2 * (size_t)b + 4;
     const size_t need = sizeof(float) * nfloat;
-    if (need > g_ws2_bytes) {
-        if (g_ws2) cudaFree(g_ws2);
-        g_ws2 = nullptr; g_ws2_bytes = 0;
-        cudaError_t e = cudaMalloc(&g_ws2, need);
+    if (need > g_ws2_bytes[slot]) {
+        if (g_ws2[slot]) { cudaDeviceSynchronize(); cudaFree(g_ws2[slot]); }
+        g_ws2[slot] = nullptr; g_ws2_bytes[slot] = 0;
+        cudaError_t e = cudaMalloc(&g_ws2[slot], need);
         if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(cudaMalloc)", e);
-        g_ws2_bytes = need;
+        g_ws2_bytes[slot] = need;
     }
-    float *d_x1 = g_ws2, *d_x2 = d_x1 + 3 * s1, *d_g1 = d_x2 + 3 * s2, *d_g2 = d_g1 + 3 * s1;
+    float *const ws = g_ws2[slot];
+    float *d_x1 = ws, *d_x2 = d_x1 + 3 * s1, *d_g1 = d_x2 + 3 * s2, *d_g2 = d_g1 + 3 * s1;
     float *d_d1 = d_g2 + 3 * s2, *d_d2 = d_d1 + s1;
     int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
     float *d_sums = reinterpret_cast<float *>(d_i2 + s2), *d_loss = d_sums + 2 * (size_t)b;
@@ -251,6 +262,7 @@ int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, i
     if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(D2H)", e);
     if (gradxyz1_dev) *gradxyz1_dev = d_g1;
     if (gradxyz2_dev) *gradxyz2_dev = d_g2;
+    if (!sync) return 1;   // asynchronous: the caller synchronises `stream` before it reads loss_host / the gradients
     return finish("psd_chamfer_loss_step_host(sync)", cudaStreamSynchronize(stream));
 }
 

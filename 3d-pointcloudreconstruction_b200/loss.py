@@ -92,3 +92,39 @@ def chamfer_loss_step_host(pred_host, gt_host, want_grads=False, stream=None):
         None, None, ctypes.c_void_p(s.cuda_stream))
     _lib.raise_on_cuda_error(rc, "psd_chamfer_loss_step_host")
     return (loss.value, g1, g2) if want_grads else loss.value
+
+
+class ChamferLossPipeline:
+    """Double-buffered form of chamfer_loss_step_host for a training loop: submit(pred_host, gt_host) enqueues one step
+    (H2D, forward, fused mean loss, backward, loss D2H) on one of two streams / workspaces and returns at once; result()
+    waits for the OLDEST submitted step and returns its loss.  With one step in flight behind the current one, the H2D copy
+    of step s+1 overlaps the kernels of step s (psd_chamfer_loss_step_host_ex with sync = 0)."""
+
+    def __init__(self, device=None):
+        import collections
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.dev):
+            self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self.loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.pending = collections.deque()
+        self.n = 0
+
+    def submit(self, pred_host, gt_host):
+        import ctypes
+        assert len(self.pending) < 2, "at most two steps in flight: call result() first"
+        slot = self.n & 1
+        self.n += 1
+        b, n, _ = pred_host.shape
+        m = gt_host.shape[1]
+        with torch.cuda.device(self.dev):
+            rc = _lib.lib.psd_chamfer_loss_step_host_ex(
+                ctypes.c_void_p(pred_host.data_ptr()), ctypes.c_void_p(gt_host.data_ptr()), b, n, m,
+                ctypes.c_void_p(self.loss.data_ptr() + 4 * slot), None, None, None, None, slot, 0,
+                ctypes.c_void_p(self.streams[slot].cuda_stream))
+        _lib.raise_on_cuda_error(rc, "psd_chamfer_loss_step_host_ex")
+        self.pending.append(slot)
+
+    def result(self):
+        slot = self.pending.popleft()
+        self.streams[slot].synchronize()
+        return float(self.loss[slot])

@@ -141,6 +141,12 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
 int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
                                float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
                                void *stream);
+/* The same step on workspace `slot` (0 or 1); with sync == 0 the call only enqueues the work on `stream` and returns, so a
+ * training loop can overlap the H2D copy of step s+1 (slot/stream B) with the kernels of step s (slot/stream A).  The caller
+ * synchronises the stream before reading loss_host (which must then be pinned) or the gradients. */
+int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                                  int slot, int sync, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py; not part of the reference surface).

@@ -165,6 +165,26 @@ def test_host_buffer_loss_step(pkg, oracle, cuda):
     assert isinstance(pkg.chamfer_loss_step_host(hx, hy), float)
 
 
+def test_host_buffer_loss_pipeline(pkg, oracle, cuda):
+    """ChamferLossPipeline (psd_chamfer_loss_step_host_ex, sync=0): double-buffered steps return each step's own loss."""
+    b, n, m = 2, 512, 768
+    steps = []
+    for seed in range(5):
+        x, y = make_clouds("uniform", b, n, m, seed=100 + seed)
+        d1, d2, _, _ = oracle.chamfer_forward(x, y, nthreads=4)
+        steps.append((torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(),
+                      d1.astype(np.float64).mean() + d2.astype(np.float64).mean()))
+    pipe = pkg.ChamferLossPipeline(cuda)
+    got = []
+    for s, (hx, hy, _) in enumerate(steps):
+        pipe.submit(hx, hy)
+        if s > 0:
+            got.append(pipe.result())
+    got.append(pipe.result())
+    for g, (_, _, want) in zip(got, steps):
+        assert abs(g - want) <= 1e-5 * abs(want)
+
+
 def test_backward_raw_accumulates_into_given_buffers(pkg, oracle, cuda):
     """chamfer_3D.backward adds onto the caller's buffers (the reference relies on caller-zeroed grads)."""
     x, y = make_clouds("uniform", 2, 256, 300, seed=21)

@@ -1,5 +1,6 @@
 // psd_capi.cu -- extern "C" surface of libpsd_b200.so (declared in include/psd_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/psd_b200.h"
@@ -207,34 +208,15 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
 
 // fwd + fused mean loss + bwd of one training step with HOST inputs: the end-to-end form of Loss.get_chamfer_loss
 // (loss/loss.py:30-37) followed by loss.backward().  Gradients stay on the device unless host pointers are given.
-static float *g_ws2[2] = {nullptr, nullptr};
-static size_t g_ws2_bytes[2] = {0, 0};
-int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
-                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
-                                  int slot, int sync, void *stream_);
-int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
-                               float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
-                               void *stream_) {
-    return psd_chamfer_loss_step_host_ex(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, gradxyz1_dev,
-                                         gradxyz2_dev, 0, 1, stream_);
-}
-int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
-                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
-                                  int slot, int sync, void *stream_) {
-    if (slot != 0 && slot != 1) { psd_set_error_msg("psd_chamfer_loss_step_host_ex: slot must be 0 or 1"); return -1; }
-    cudaStream_t stream = (cudaStream_t)stream_;
+static const int kStepSlots = 8;
+static float *g_ws2[kStepSlots] = {};
+static size_t g_ws2_bytes[kStepSlots] = {};
+
+// One training step's stream work (H2D, memsets, forward, mean loss, backward, D2H) for a given workspace.
+static cudaError_t enqueue_loss_step(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                     float *gradxyz1_host, float *gradxyz2_host, float *ws, cudaStream_t stream) {
     const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
     // layout: xyz1 | xyz2 | grad1 | grad2 | dist1 | dist2 | idx1 | idx2 | sums[2b] | loss
-    const size_t nfloat = 6 * (s1 + s2) + 2 * (s1 + s2) + 2 * (size_t)b + 4;
-    const size_t need = sizeof(float) * nfloat;
-    if (need > g_ws2_bytes[slot]) {
-        if (g_ws2[slot]) { cudaDeviceSynchronize(); cudaFree(g_ws2[slot]); }
-        g_ws2[slot] = nullptr; g_ws2_bytes[slot] = 0;
-        cudaError_t e = cudaMalloc(&g_ws2[slot], need);
-        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(cudaMalloc)", e);
-        g_ws2_bytes[slot] = need;
-    }
-    float *const ws = g_ws2[slot];
     float *d_x1 = ws, *d_x2 = d_x1 + 3 * s1, *d_g1 = d_x2 + 3 * s2, *d_g2 = d_g1 + 3 * s1;
     float *d_d1 = d_g2 + 3 * s2, *d_d2 = d_d1 + s1;
     int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
@@ -247,23 +229,141 @@ int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host
         e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_x2, xyz2_host, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
     }
-    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(H2D)", e);
+    if (e != cudaSuccess) return e;
     // gradients and per-cloud sums start from zero: one memset each (grad1|grad2 are adjacent)
     if ((e = cudaMemsetAsync(d_g1, 0, sizeof(float) * 3 * (s1 + s2), stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(d_sums, 0, sizeof(float) * (2 * (size_t)b + 1), stream)) != cudaSuccess)
-        return finish("psd_chamfer_loss_step_host(memset)", e);
+        return e;
     e = psd_launch_chamfer_forward(d_x1, d_x2, b, n, m, 0, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream);
     if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(d_sums, b, n, m, d_loss, stream);
     if (e == cudaSuccess) e = psd_launch_chamfer_backward(d_x1, d_x2, d_g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, stream, nullptr);
-    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(launch)", e);
+    if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && gradxyz1_host) e = cudaMemcpyAsync(gradxyz1_host, d_g1, sizeof(float) * 3 * s1, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && gradxyz2_host) e = cudaMemcpyAsync(gradxyz2_host, d_g2, sizeof(float) * 3 * s2, cudaMemcpyDeviceToHost, stream);
-    if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(D2H)", e);
-    if (gradxyz1_dev) *gradxyz1_dev = d_g1;
-    if (gradxyz2_dev) *gradxyz2_dev = d_g2;
+    return e;
+}
+
+// A training loop calls the step with the same few pinned staging buffers over and over: the second time a
+// (buffers, shape, workspace) combination is seen its stream work is captured into a CUDA graph, and from then on one
+// cudaGraphLaunch replaces the nine API calls of a step (the host side, not the GPU, bounds a 40 µs step otherwise).
+struct StepGraph {
+    const void *x1 = nullptr, *x2 = nullptr, *loss = nullptr, *g1 = nullptr, *g2 = nullptr, *ws = nullptr;
+    int b = 0, n = 0, m = 0, variant = 0, device = -1;
+    cudaGraphExec_t exec = nullptr;
+    bool plain = false;   // capture was not possible (pageable buffers, stream already capturing): keep the plain path
+    unsigned long long last_use = 0;
+    bool same(const StepGraph &o) const {
+        return x1 == o.x1 && x2 == o.x2 && loss == o.loss && g1 == o.g1 && g2 == o.g2 && ws == o.ws && b == o.b && n == o.n &&
+               m == o.m && variant == o.variant && device == o.device;
+    }
+};
+static const int kStepGraphs = 64;
+static StepGraph g_step_graph[kStepGraphs];
+static unsigned long long g_step_clock = 0;
+static int g_step_graph_enabled = -1;   // -1: read PSD_HOST_STEP_GRAPH on first use
+
+static void drop_step_graphs(const void *ws) {
+    for (StepGraph &g : g_step_graph)
+        if (g.ws == ws) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = StepGraph();
+        }
+}
+
+static bool pinned_host(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int psd_host_step_graphs(int enable) {
+    const int old = g_step_graph_enabled;
+    if (enable == 0 || enable == 1) g_step_graph_enabled = enable;
+    return old;
+}
+
+int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                                  int slot, int sync, void *stream_) {
+    if (slot < 0 || slot >= kStepSlots) { psd_set_error_msg("psd_chamfer_loss_step_host_ex: slot must be 0..7"); return -1; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
+    const size_t nfloat = 6 * (s1 + s2) + 2 * (s1 + s2) + 2 * (size_t)b + 4;
+    const size_t need = sizeof(float) * nfloat;
+    if (need > g_ws2_bytes[slot]) {
+        if (g_ws2[slot]) { cudaDeviceSynchronize(); drop_step_graphs(g_ws2[slot]); cudaFree(g_ws2[slot]); }
+        g_ws2[slot] = nullptr; g_ws2_bytes[slot] = 0;
+        cudaError_t e = cudaMalloc(&g_ws2[slot], need);
+        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(cudaMalloc)", e);
+        g_ws2_bytes[slot] = need;
+    }
+    float *const ws = g_ws2[slot];
+    if (gradxyz1_dev) *gradxyz1_dev = ws + 3 * (s1 + s2);
+    if (gradxyz2_dev) *gradxyz2_dev = ws + 3 * (s1 + s2) + 3 * s1;
+
+    if (g_step_graph_enabled < 0) {
+        const char *env = getenv("PSD_HOST_STEP_GRAPH");
+        g_step_graph_enabled = (env && env[0] == '0') ? 0 : 1;
+    }
+    bool launched = false;
+    if (g_step_graph_enabled && stream != nullptr && stream != cudaStreamLegacy) {
+        StepGraph key;
+        key.x1 = xyz1_host; key.x2 = xyz2_host; key.loss = loss_host; key.g1 = gradxyz1_host; key.g2 = gradxyz2_host;
+        key.ws = ws; key.b = b; key.n = n; key.m = m; key.variant = psd_set_nn_variant(-1);
+        cudaGetDevice(&key.device);
+        StepGraph *hit = nullptr, *victim = &g_step_graph[0];
+        for (StepGraph &g : g_step_graph) {
+            if (g.ws && g.same(key)) { hit = &g; break; }
+            if (g.last_use < victim->last_use) victim = &g;
+        }
+        if (hit == nullptr) {   // first sighting: remember the combination, run the plain path below
+            if (victim->exec) cudaGraphExecDestroy(victim->exec);
+            *victim = key;
+            victim->last_use = ++g_step_clock;
+        } else {
+            hit->last_use = ++g_step_clock;
+            if (hit->exec == nullptr && !hit->plain &&
+                !(pinned_host(xyz1_host) && pinned_host(xyz2_host) && pinned_host(loss_host) && pinned_host(gradxyz1_host) &&
+                  pinned_host(gradxyz2_host)))
+                hit->plain = true;
+            if (hit->exec == nullptr && !hit->plain) {
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+                if (e == cudaSuccess) {
+                    e = enqueue_loss_step(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, ws, stream);
+                    cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
+                    if (e == cudaSuccess) e = e2;
+                }
+                if (e == cudaSuccess) e = cudaGraphInstantiate(&hit->exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    hit->exec = nullptr;
+                    hit->plain = true;
+                }
+            }
+            if (hit->exec) {
+                cudaError_t e = cudaGraphLaunch(hit->exec, stream);
+                if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(graph launch)", e);
+                launched = true;
+            }
+        }
+    }
+    if (!launched) {
+        cudaError_t e = enqueue_loss_step(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, ws, stream);
+        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(enqueue)", e);
+    }
     if (!sync) return 1;   // asynchronous: the caller synchronises `stream` before it reads loss_host / the gradients
     return finish("psd_chamfer_loss_step_host(sync)", cudaStreamSynchronize(stream));
+}
+
+int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                               float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                               void *stream_) {
+    return psd_chamfer_loss_step_host_ex(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, gradxyz1_dev,
+                                         gradxyz2_dev, 0, 1, stream_);
 }
 
 }  // extern "C"

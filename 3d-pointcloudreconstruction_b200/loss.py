@@ -95,24 +95,28 @@ def chamfer_loss_step_host(pred_host, gt_host, want_grads=False, stream=None):
 
 
 class ChamferLossPipeline:
-    """Double-buffered form of chamfer_loss_step_host for a training loop: submit(pred_host, gt_host) enqueues one step
-    (H2D, forward, fused mean loss, backward, loss D2H) on one of two streams / workspaces and returns at once; result()
-    waits for the OLDEST submitted step and returns its loss.  With one step in flight behind the current one, the H2D copy
-    of step s+1 overlaps the kernels of step s (psd_chamfer_loss_step_host_ex with sync = 0)."""
+    """Pipelined form of chamfer_loss_step_host for a training loop: submit(pred_host, gt_host) enqueues one step
+    (H2D, forward, fused mean loss, backward, loss D2H) on one of `depth` streams / workspaces and returns at once; result()
+    waits for the OLDEST submitted step and returns its loss.  With depth = 3 (the default, at most 8) the H2D copy of a
+    step and the host's own latency between two submits hide behind the kernels of the two steps before it
+    (psd_chamfer_loss_step_host_ex with sync = 0); depth = 2 still exposes the host latency at config 2
+    (tools/e2e_timeline.py)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, depth=3):
         import collections
+        assert 1 <= depth <= 8
+        self.depth = depth
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         with torch.cuda.device(self.dev):
-            self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        self.loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+            self.streams = [torch.cuda.Stream() for _ in range(depth)]
+        self.loss = torch.zeros(depth, dtype=torch.float32).pin_memory()
         self.pending = collections.deque()
         self.n = 0
 
     def submit(self, pred_host, gt_host):
         import ctypes
-        assert len(self.pending) < 2, "at most two steps in flight: call result() first"
-        slot = self.n & 1
+        assert len(self.pending) < self.depth, "pipeline full: call result() first"
+        slot = self.n % self.depth
         self.n += 1
         b, n, _ = pred_host.shape
         m = gt_host.shape[1]

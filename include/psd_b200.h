@@ -141,12 +141,18 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
 int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
                                float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
                                void *stream);
-/* The same step on workspace `slot` (0 or 1); with sync == 0 the call only enqueues the work on `stream` and returns, so a
- * training loop can overlap the H2D copy of step s+1 (slot/stream B) with the kernels of step s (slot/stream A).  The caller
+/* The same step on workspace `slot` (0..7); with sync == 0 the call only enqueues the work on `stream` and returns, so a
+ * training loop can keep several steps in flight, each on its own slot and stream: the H2D copy of step s+2 and the host's
+ * own latency (wake-up after step s-1, the next call) then hide behind the kernels of steps s and s+1.  The caller
  * synchronises the stream before reading loss_host (which must then be pinned) or the gradients. */
 int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
                                   float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
                                   int slot, int sync, void *stream);
+/* Repeated calls of the host step with the same pinned buffers, shape, slot and a non-default stream are replayed from a
+ * cached CUDA graph (one cudaGraphLaunch instead of nine API calls per step) from the second sighting on; pageable
+ * buffers and the default stream always take the plain path.  enable: 0 / 1 sets it, anything else only queries;
+ * returns the previous setting (-1 = not decided yet: env PSD_HOST_STEP_GRAPH=0 disables).  The result is identical. */
+int psd_host_step_graphs(int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (used by bench.py; not part of the reference surface).

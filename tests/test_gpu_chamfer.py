@@ -185,6 +185,43 @@ def test_host_buffer_loss_pipeline(pkg, oracle, cuda):
         assert abs(g - want) <= 1e-5 * abs(want)
 
 
+@pytest.mark.parametrize("depth", [2, 3, 4])
+def test_host_buffer_loss_pipeline_graph_replay(pkg, oracle, cuda, depth):
+    """The same pinned staging buffers submitted again and again are replayed from a cached CUDA graph
+    (psd_host_step_graphs): the loss must follow the buffers' CURRENT contents and agree with the plain path."""
+    from importlib import import_module
+    lib = import_module(pkg.__name__ + "._lib").lib
+    b, n, m = 2, 640, 512
+    bufs = [(torch.empty(b, n, 3).pin_memory(), torch.empty(b, m, 3).pin_memory()) for _ in range(depth)]
+    data = [make_clouds("uniform", b, n, m, seed=300 + s) for s in range(4 * depth)]
+    want = []
+    for x, y in data:
+        d1, d2, _, _ = oracle.chamfer_forward(x, y, nthreads=4)
+        want.append(d1.astype(np.float64).mean() + d2.astype(np.float64).mean())
+    results = {}
+    for graphs in (1, 0):
+        old = lib.psd_host_step_graphs(graphs)
+        try:
+            pipe = pkg.ChamferLossPipeline(cuda, depth=depth)
+            got = []
+            for s, (x, y) in enumerate(data):
+                if s >= depth:
+                    got.append(pipe.result())   # the step that used this buffer pair has finished: safe to overwrite
+                hx, hy = bufs[s % depth]
+                hx.copy_(torch.from_numpy(x)); hy.copy_(torch.from_numpy(y))
+                pipe.submit(hx, hy)
+            while pipe.pending:
+                got.append(pipe.result())
+        finally:
+            lib.psd_host_step_graphs(old if old in (0, 1) else 1)
+        results[graphs] = got
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert abs(g - w) <= 1e-5 * abs(w)
+    for g0, g1 in zip(results[0], results[1]):   # the per-cloud sums are float atomics: equal up to summation order
+        assert abs(g0 - g1) <= 1e-6 * abs(g0)
+
+
 def test_backward_raw_accumulates_into_given_buffers(pkg, oracle, cuda):
     """chamfer_3D.backward adds onto the caller's buffers (the reference relies on caller-zeroed grads)."""
     x, y = make_clouds("uniform", 2, 256, 300, seed=21)

@@ -11,6 +11,7 @@ There is no CPU fallback: importing `_lib` raises if libpsd_b200.so is missing.
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is absent)
 from . import chamfer_3D, emd  # native-module mirrors (pybind names of the reference)
 from . import proj_loss        # loss/proj_loss.py mirror (get_loss_proj, grid_dist)
+from . import icp              # utils/icp.py mirror (icp, best_fit_transform, nearest_neighbor) + icp_batch
 from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction
 from .emd_module import emdFunction, emdModule
 from .fscore import fscore, chamfer_fscore_fused
@@ -18,6 +19,6 @@ from .loss import Loss, chamfer_loss_step_host, ChamferLossPipeline
 from .metrics import Metrics
 
 __all__ = [
-    "chamfer_3D", "emd", "proj_loss", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
+    "chamfer_3D", "emd", "proj_loss", "icp", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
     "fscore", "chamfer_fscore_fused", "Loss", "chamfer_loss_step_host", "ChamferLossPipeline", "Metrics",
 ]

@@ -16,6 +16,11 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
 cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m, float *out, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
 int psd_set_nn_variant(int v);
+cudaError_t psd_launch_icp(const void *a, const void *b, int in_f64, int batch, int n, const double *init_pose, int max_iter,
+                           double tol, double *T, double *dist, int *iters, cudaStream_t stream);
+cudaError_t psd_launch_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances,
+                              int *indices, cudaStream_t stream);
+int psd_icp_max_points();
 cudaError_t psd_launch_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode,
                                      float *out_min, float *out_inv, cudaStream_t stream);
 void psd_set_tc_debug(float *dbg, int ld);
@@ -146,6 +151,21 @@ int psd_proj_min_dist(const float *pred, const float *gt, const float *table, in
     if (mode != 0 && mode != 1) { psd_set_error_msg("psd_proj_min_dist: mode must be 0 (as written) or 1 (intended)"); return -1; }
     if ((size_t)h * w * 8 > 200 * 1024) { psd_set_error_msg("psd_proj_min_dist: grid too large for the shared-memory table (h*w <= 25600)"); return -1; }
     return finish("psd_proj_min_dist", psd_launch_proj_min_dist(pred, gt, table, b, h, w, mode, min_dist, min_dist_inv, (cudaStream_t)stream));
+}
+
+int psd_icp_batch(const void *a, const void *b, int in_f64, int batch, int n, const double *init_pose, int max_iterations,
+                  double tolerance, double *T_out, double *distances, int *iterations, void *stream) {
+    if (batch < 0 || n < 1 || max_iterations < 0) { psd_set_error_msg("psd_icp_batch: batch >= 0, n >= 1, max_iterations >= 0 required"); return -1; }
+    if (n > psd_icp_max_points()) { psd_set_error_msg("psd_icp_batch: n exceeds the shared-memory resident limit (4096 points)"); return -1; }
+    return finish("psd_icp_batch", psd_launch_icp(a, b, in_f64, batch, n, init_pose, max_iterations, tolerance, T_out, distances,
+                                                  iterations, (cudaStream_t)stream));
+}
+
+int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances, int *indices,
+               void *stream) {
+    if (batch < 0 || n_src < 0 || n_dst < 1) { psd_set_error_msg("psd_nn_f64: batch >= 0, n_src >= 0, n_dst >= 1 required"); return -1; }
+    if ((size_t)n_dst * 24 > 200 * 1024) { psd_set_error_msg("psd_nn_f64: destination cloud too large for shared memory (n_dst <= 8533)"); return -1; }
+    return finish("psd_nn_f64", psd_launch_nn_f64(src, dst, in_f64, batch, n_src, n_dst, distances, indices, (cudaStream_t)stream));
 }
 
 int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }

@@ -127,6 +127,25 @@ int psd_proj_min_dist(const float *pred, const float *gt, const float *table, in
                       float *min_dist_inv, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * psd_icp_batch  =  icp(A, B, init_pose, max_iterations, tolerance) of utils/icp.py:68-118 for a whole batch in ONE launch
+ * (the reference runs it per sample on the CPU: testnet.py:62-64, test_pix3d.py:62-64, tolerance 1e-10, 1024 iterations).
+ * a, b: [batch, n, 3] source / destination clouds on the device, fp32 (in_f64 = 0) or fp64 (in_f64 = 1); n <= 4096.
+ * init_pose: optional device 4x4 fp64 row-major rigid transform (last row 0 0 0 1) applied to every source, or NULL.
+ * Each sample iterates NN (nearest_neighbor, :49-65) -> best_fit_transform (:4-46) -> src = T src until
+ * |prev_error - mean_error| < tolerance or max_iterations, on its own.  Outputs (device): T_out [batch,4,4] fp64 row-major =
+ * best_fit_transform(A, final src); distances [batch,n] fp64 (last NN pass; may be NULL); iterations [batch] = the
+ * reference's returned `i` (may be NULL).  max_iterations = 0 returns best_fit_transform(A, B) of the given correspondences.
+ * All arithmetic is fp64.  Returns 1 ok / 0 CUDA error / -1 argument error.
+ *
+ * psd_nn_f64  =  nearest_neighbor(src, dst) (utils/icp.py:49-65) for a batch: distances [batch,n_src] fp64 (Euclidean, not
+ * squared) and indices [batch,n_src] int32 into dst; n_dst <= 8533.
+ * ------------------------------------------------------------------------------------------- */
+int psd_icp_batch(const void *a, const void *b, int in_f64, int batch, int n, const double *init_pose, int max_iterations,
+                  double tolerance, double *T_out, double *distances, int *iterations, void *stream);
+int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances, int *indices,
+               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
  * stages them through its own device workspace on `stream` and copies the results back).
  * ------------------------------------------------------------------------------------------- */

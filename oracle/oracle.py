@@ -345,3 +345,74 @@ def proj_min_dist(pred, gt, dist_mat, mode="as_written"):
         a = ((gt_th[:, None, None, :, :] * d[None]).astype(np.float32) * pred[:, :, :, None, None]).astype(np.float32)
         c = ((pred_mask[:, None, None, :, :] * d[None]).astype(np.float32) * gt[:, :, :, None, None]).astype(np.float32)
     return a.min(axis=(3, 4)), c.min(axis=(3, 4))      # np.min propagates NaN like torch.min
+
+
+# ---------------------------------------------------------------------------------------------
+# ICP alignment (utils/icp.py) -- numpy restatement; the KD-tree query is replaced by the fp64 brute force it is
+# equivalent to (reduced distance = sum of squared differences in axis order, first index on ties).
+# Pinned by tests/golden/icp_*_ref.npz, produced by the reference's own icp() (sklearn KD-tree) in
+# tests/golden/make_golden_icp.py.
+# ---------------------------------------------------------------------------------------------
+def icp_best_fit_transform(A, B):
+    """utils/icp.py:4-46.  Like the reference, the inputs keep their dtype: icp()'s final call passes the caller's float32 A
+    next to the float64 moved source, so centroid_A and AA are float32 arithmetic there (np.mean over axis 0 of a
+    C-contiguous [N,3] array accumulates row after row in the array's dtype)."""
+    A = np.asarray(A)
+    B = np.asarray(B)
+    assert A.shape == B.shape
+    m = A.shape[1]
+    centroid_A = np.mean(A, axis=0)
+    centroid_B = np.mean(B, axis=0)
+    AA = A - centroid_A
+    BB = B - centroid_B
+    H = np.dot(AA.T, BB)                       # :27
+    U, S, Vt = np.linalg.svd(H)                # :28
+    R = np.dot(Vt.T, U.T)                      # :29
+    if np.linalg.det(R) < 0:                   # :32-35 reflection case
+        Vt[m - 1, :] *= -1
+        R = np.dot(Vt.T, U.T)
+    t = centroid_B.T - np.dot(R, centroid_A.T)  # :38
+    T = np.identity(m + 1)
+    T[:m, :m] = R
+    T[:m, m] = t
+    return T, R, t
+
+
+def icp_nearest_neighbor(src, dst):
+    """utils/icp.py:49-65 (NearestNeighbors(n_neighbors=1).fit(dst).kneighbors(src)), as an fp64 brute force."""
+    src = np.asarray(src, dtype=np.float64)
+    dst = np.asarray(dst, dtype=np.float64)
+    dist = np.empty(src.shape[0])
+    idx = np.empty(src.shape[0], dtype=np.int64)
+    for s in range(0, src.shape[0], 512):
+        d = dst[None, :, :] - src[s:s + 512, None, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        k = np.argmin(d2, axis=1)
+        idx[s:s + 512] = k
+        dist[s:s + 512] = np.sqrt(d2[np.arange(d2.shape[0]), k])
+    return dist, idx
+
+
+def icp(A, B, init_pose=None, max_iterations=20, tolerance=0.001):
+    """utils/icp.py:68-118."""
+    A = np.asarray(A)
+    B = np.asarray(B)
+    assert A.shape == B.shape
+    m = A.shape[1]
+    src = np.ones((m + 1, A.shape[0]))
+    dst = np.ones((m + 1, B.shape[0]))
+    src[:m, :] = np.copy(A.T)
+    dst[:m, :] = np.copy(B.T)
+    if init_pose is not None:
+        src = np.dot(init_pose, src)
+    prev_error = 0
+    for i in range(max_iterations):
+        distances, indices = icp_nearest_neighbor(src[:m, :].T, dst[:m, :].T)      # :98
+        T, _, _ = icp_best_fit_transform(src[:m, :].T, dst[:m, indices].T)         # :101
+        src = np.dot(T, src)                                                        # :104
+        mean_error = np.mean(distances)                                             # :107
+        if np.abs(prev_error - mean_error) < tolerance:
+            break
+        prev_error = mean_error
+    T, _, _ = icp_best_fit_transform(A, src[:m, :].T)                               # :113
+    return T, distances, i

@@ -21,6 +21,10 @@ cudaError_t psd_launch_icp(const void *a, const void *b, int in_f64, int batch, 
 cudaError_t psd_launch_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances,
                               int *indices, cudaStream_t stream);
 int psd_icp_max_points();
+cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
+                                 cudaStream_t stream);
+cudaError_t psd_launch_fps(const float *xyz, int b, int n, int npoint, int start, long long *centroids, cudaStream_t stream);
+int psd_fps_max_points();
 cudaError_t psd_launch_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode,
                                      float *out_min, float *out_inv, cudaStream_t stream);
 void psd_set_tc_debug(float *dbg, int ld);
@@ -159,6 +163,18 @@ int psd_icp_batch(const void *a, const void *b, int in_f64, int batch, int n, co
     if (n > psd_icp_max_points()) { psd_set_error_msg("psd_icp_batch: n exceeds the shared-memory resident limit (4096 points)"); return -1; }
     return finish("psd_icp_batch", psd_launch_icp(a, b, in_f64, batch, n, init_pose, max_iterations, tolerance, T_out, distances,
                                                   iterations, (cudaStream_t)stream));
+}
+
+int psd_farthest_point_sample(const float *xyz, int b, int n, int npoint, int start, long long *centroids, void *stream) {
+    if (b < 0 || n < 1 || npoint < 0) { psd_set_error_msg("psd_farthest_point_sample: b >= 0, n >= 1, npoint >= 0 required"); return -1; }
+    if (start < 0 || start >= n) { psd_set_error_msg("psd_farthest_point_sample: start index outside the cloud"); return -1; }
+    if (n > psd_fps_max_points()) { psd_set_error_msg("psd_farthest_point_sample: n exceeds the shared-memory resident limit (16384 points)"); return -1; }
+    return finish("psd_farthest_point_sample", psd_launch_fps(xyz, b, n, npoint, start, centroids, (cudaStream_t)stream));
+}
+
+int psd_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out, void *stream) {
+    if (b < 0 || n < 0 || grid_h < 1 || grid_w < 1) { psd_set_error_msg("psd_cont_proj: b, n >= 0 and grid_h, grid_w >= 1 required"); return -1; }
+    return finish("psd_cont_proj", psd_launch_cont_proj(pcl, b, n, grid_h, grid_w, sigma_sq, out, (cudaStream_t)stream));
 }
 
 int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances, int *indices,

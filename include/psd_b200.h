@@ -146,6 +146,27 @@ int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_sr
                void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * psd_farthest_point_sample  =  farthest_point_sample(xyz, npoint, RAN) of utils/utils.py:335-360 (called by the dataset
+ * for the 128- and 256-point ground-truth clouds, utils/datasets_sample_pcl.py:87-91).
+ * xyz: [B, N, 3] fp32 device; centroids: [B, npoint] int64 device (the reference returns torch.long).  start = the first
+ * centroid: the reference draws torch.randint(0, 1) = 0 when RAN is true and torch.randint(1, 2) = 1 otherwise.
+ * Distances are fp32 ((dx*dx + dy*dy) + dz*dz, no contraction), ties go to the lowest index: the indices are bit-identical
+ * to the reference's on the CPU.  N <= 16384.  Returns 1 ok / 0 CUDA error / -1 argument error.
+ * ------------------------------------------------------------------------------------------- */
+int psd_farthest_point_sample(const float *xyz, int b, int n, int npoint, int start, long long *centroids, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * psd_cont_proj  =  cont_proj(pcl, grid_h, grid_w, device, sigma_sq) of utils/projection.py:4-67 (Gaussian splat of a cloud
+ * to a silhouette image; feeds get_loss_proj, utils/utils.py:232,241).
+ * pcl: [B, N, 3] fp32 device, coordinates in (-1, 1); out: [B, grid_h, grid_w] fp32 device,
+ *   out[b,h,w] = sum_p exp(-(x_p - h)^2 / (2 sigma_sq)) * exp(-(y_p - w)^2 / (2 sigma_sq)),
+ *   x_p = ((p.x + 1) * grid_h) / 2, y_p = ((p.y + 1) * grid_w) / 2,
+ * with the reference's fp32 rounding sequence and summation order (points in order); the only difference to the CPU reference
+ * is the last ulp of expf.  Returns 1 ok / 0 CUDA error / -1 argument error.
+ * ------------------------------------------------------------------------------------------- */
+int psd_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
  * stages them through its own device workspace on `stream` and copies the results back).
  * ------------------------------------------------------------------------------------------- */

@@ -416,3 +416,51 @@ def icp(A, B, init_pose=None, max_iterations=20, tolerance=0.001):
         prev_error = mean_error
     T, _, _ = icp_best_fit_transform(A, src[:m, :].T)                               # :113
     return T, distances, i
+
+
+# ---------------------------------------------------------------------------------------------
+# Farthest point sampling (utils/utils.py:335-360) and the Gaussian splat cont_proj (utils/projection.py:4-67, 95-106):
+# numpy restatements in float32, pinned by tests/golden/fps_*_ref.npz and splat_*_ref.npz which the reference's own torch
+# code produced on the CPU (tests/golden/make_golden_fps_splat.py).
+# ---------------------------------------------------------------------------------------------
+def farthest_point_sample(xyz, npoint, RAN=True):
+    """utils/utils.py:335-360.  torch.randint(0, 1) is always 0 and torch.randint(1, 2) always 1, so the first centroid is
+    index 0 (RAN) or 1 (not RAN); torch.sum over the 3 coordinates adds in axis order; torch.max returns the first maximum."""
+    xyz = np.asarray(xyz, dtype=np.float32)
+    B, N, C = xyz.shape
+    centroids = np.zeros((B, npoint), dtype=np.int64)
+    distance = np.full((B, N), 1e10, dtype=np.float32)
+    farthest = np.zeros(B, dtype=np.int64) if RAN else np.ones(B, dtype=np.int64)
+    rows = np.arange(B)
+    for i in range(npoint):
+        centroids[:, i] = farthest
+        centroid = xyz[rows, farthest, :][:, None, :]
+        d = xyz - centroid
+        sq = d * d
+        dist = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+        mask = dist < distance
+        distance[mask] = dist[mask]
+        farthest = np.argmax(distance, axis=-1)
+    return centroids
+
+
+def cont_proj(pcl, grid_h, grid_w, sigma_sq=0.5):
+    """utils/projection.py:4-67.  float32 rounding sequence of the torch expressions; exp is the correctly rounded float32
+    exponential (torch's CPU exp and CUDA's expf are both within 1-2 ulp of it); the sum runs over the points in order."""
+    pcl = np.asarray(pcl, dtype=np.float32)
+    f = np.float32
+    x = ((pcl[..., 0] + f(1)) * f(grid_h)) / f(2)
+    y = ((pcl[..., 1] + f(1)) * f(grid_w)) / f(2)
+    two_s = f(2.0 * sigma_sq)
+    hh = np.arange(grid_h, dtype=np.float32)
+    ww = np.arange(grid_w, dtype=np.float32)
+
+    def kern(d):
+        a = (-(d * d)) / two_s                       # float32
+        return np.exp(a.astype(np.float64)).astype(np.float32)
+    ex = kern(x[:, :, None] - hh[None, None, :])     # [B,N,H]
+    ey = kern(y[:, :, None] - ww[None, None, :])     # [B,N,W]
+    out = np.zeros((pcl.shape[0], grid_h, grid_w), dtype=np.float32)
+    for p in range(pcl.shape[1]):
+        out += ex[:, p, :, None] * ey[:, p, None, :]
+    return out

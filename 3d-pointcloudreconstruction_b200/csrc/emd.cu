@@ -32,6 +32,7 @@ namespace psd {
 
 constexpr int kEmdThreads = 1024;
 constexpr float kNegInit = -1e9f;
+constexpr int kSoloMax = 32;   // bidders per cloud at or below which one CTA finishes the auction alone (one warp per bidder)
 
 struct EmdParams {
     const float *xyz1, *xyz2;
@@ -46,6 +47,7 @@ struct EmdParams {
     float eps;
     int iters;
     int fresh;  // 1: ignore the caller's state tensors and start from assignment = -1, price = 0
+    int solo;   // 1: shared memory holds the solo-mode arrays (see emd_auction_kernel)
 };
 
 // float atomicMax with the reference's semantics (emd_cuda.cu:10-20): CAS loop, `val > old` in float.
@@ -73,6 +75,102 @@ __device__ __forceinline__ void merge_top2(Top2 &a, float ob, float o2, int oi) 
         a.idx = (oi >= 0 && (a.idx < 0 || oi < a.idx)) ? oi : a.idx;
     } else {
         a.better = fmaxf(a.better, ob);
+    }
+}
+
+// One bidder group's scan of all n objects: thread t of tpb (a power of two) looks at objects t, t + tpb, ... and returns its
+// partial (best, second best, index of best); the caller merges the group.
+// Scan with deferred value evaluation.  A pair can change the top two only if v > better, i.e.
+// sqrt(s) < 3 - better - price <= 3 - better (prices are >= 0): pairs with s above R2 = (3 - better + 2e-6)^2, or
+// above (3 - better - price[k] + slack)^2 once the object's price is looked at, are skipped exactly.  The survivors' values
+// (IEEE sqrt + fp64 arithmetic, ~30 instructions) used to be evaluated inside the scan, where one surviving lane sends the
+// whole warp down the long path (27-60 % of the iterations).  Now a lane queues its survivors (in index order, so the strict
+// '>' tie rule is unchanged) and the warp evaluates them together when some lane has two; `better` for the radius is then
+// the second best of the whole bidder group inside the warp (a valid lower bound of the final second best), not only the
+// lane's own.
+__device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, const float *oz, const float *price, int n,
+                                            float x1, float y1, float z1, int tpb, int t, bool valid) {
+    Top2 r;
+    r.best = kNegInit; r.better = kNegInit; r.idx = -1;
+    const int wl = tpb < 32 ? tpb : 32;
+    float R2 = 3.0e38f, Rg = 3.0e38f;   // squared / plain pruning radius from the group's second best so far
+    int qn = 0, qk0 = 0, qk1 = 0;
+    float qs0 = 0.f, qs1 = 0.f;
+    auto apply = [&](int k, float v) {
+        if (v > r.best) {
+            r.better = r.best; r.best = v; r.idx = k;
+        } else if (v > r.better) {
+            r.better = v;
+        }
+    };
+    auto evaluate_queue = [&]() {
+        // both values first (two independent sqrt / fp64 chains in flight), then the updates in index order
+        const float v0 = (float)(3.0 - (double)__fsqrt_rn(qs0) - (double)price[qk0]);
+        const float v1 = (float)(3.0 - (double)__fsqrt_rn(qs1) - (double)price[qk1]);
+        if (qn > 0) apply(qk0, v0);
+        if (qn > 1) apply(qk1, v1);
+        qn = 0;
+    };
+    auto flush = [&]() {   // warp-uniform
+        evaluate_queue();
+        float gb = r.best, g2 = r.better;   // group-wide (best, second best with multiplicity) so far
+        for (int o = wl >> 1; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, gb, o);
+            const float o2 = __shfl_xor_sync(0xffffffffu, g2, o);
+            g2 = fmaxf(fminf(gb, ob), fmaxf(g2, o2));
+            gb = fmaxf(gb, ob);
+        }
+        Rg = 3.0f - g2;
+        const float R = Rg + 2e-6f;
+        R2 = R * R * 1.000001f;
+    };
+    // n is a multiple of 1024 and tpb a power of two <= 1024: every lane of the warp runs n / tpb iterations
+    auto consider = [&](int k, float s, bool pass) {   // warp-uniform call; `pass` = survived the price-free test
+        if (pass) {
+            // per-object test with the object's own price: v > better needs sqrt(s) < 3 - better - price[k].  The
+            // slack covers the fp32 rounding of this test and of the reference's value (|terms| are O(1): 3 ulp(4)).
+            const float pk = price[k];
+            const float Rk = (Rg - pk) + (4e-6f + 1e-6f * (fabsf(Rg) + fabsf(pk)));
+            if (Rk > 0.f && s <= Rk * Rk * 1.000002f) {
+                if (qn == 0) { qk0 = k; qs0 = s; } else { qk1 = k; qs1 = s; }
+                ++qn;
+            }
+        }
+        if (__any_sync(0xffffffffu, qn == 2)) flush();
+    };
+    if (((n / tpb) & 3) == 0) {
+        // four objects per lane and step: 12 shared-memory loads in flight, one vote for the common all-skipped case
+        const int st = tpb;
+        for (int k = t; k < n; k += 4 * st) {
+            const float s0 = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+            const float s1 = sqdist_exact(ox[k + st] - x1, oy[k + st] - y1, oz[k + st] - z1);
+            const float s2 = sqdist_exact(ox[k + 2 * st] - x1, oy[k + 2 * st] - y1, oz[k + 2 * st] - z1);
+            const float s3 = sqdist_exact(ox[k + 3 * st] - x1, oy[k + 3 * st] - y1, oz[k + 3 * st] - z1);
+            const bool p0 = valid && s0 <= R2, p1 = valid && s1 <= R2, p2 = valid && s2 <= R2, p3 = valid && s3 <= R2;
+            if (__any_sync(0xffffffffu, p0 || p1 || p2 || p3)) {
+                consider(k, s0, p0);
+                consider(k + st, s1, p1);
+                consider(k + 2 * st, s2, p2);
+                consider(k + 3 * st, s3, p3);
+            }
+        }
+    } else {
+        for (int k = t; k < n; k += tpb) {
+            const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+            consider(k, s, valid && s <= R2);
+        }
+    }
+    if (__any_sync(0xffffffffu, qn > 0)) evaluate_queue();   // what is still queued; no radius is needed any more
+    return r;
+}
+
+// merge of a bidder group's partial results inside a warp (over min(tpb, 32) lanes)
+__device__ __forceinline__ void warp_merge_top2(Top2 &r, int wl) {
+    for (int o = wl >> 1; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, r.best, o);
+        const float o2 = __shfl_xor_sync(0xffffffffu, r.better, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, r.idx, o);
+        merge_top2(r, ob, o2, oi);
     }
 }
 
@@ -104,6 +202,18 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     int *w_idx = reinterpret_cast<int *>(w_better + 32);
     int *ucount = w_idx + 32;                                   // [8] bidder count of every rank
     int *cnt = ucount + 8;                                      // [1]
+    // solo mode (only rank 0's copies are used): the whole cloud's sliced state gathered into full-length arrays
+    float *F_maxinc = reinterpret_cast<float *>(cnt + 4);       // [n]
+    int *F_winner = reinterpret_cast<int *>(F_maxinc + n);      // [n]
+    int *F_inv = F_winner + n;                                  // [n]
+    int *F_assign = F_inv + n;                                  // [n]
+    int *F_bid = F_assign + n;                                  // [n]
+    float *F_binc = reinterpret_cast<float *>(F_bid + n);       // [n]
+    int *s_list = reinterpret_cast<int *>(F_binc + n);          // [2][kSoloMax] bidder lists (global point indices)
+    int *s_cnt = s_list + 2 * kSoloMax;                         // [2]
+    int *s_sbid = s_cnt + 2;                                    // [kSoloMax]
+    float *s_sinc = reinterpret_cast<float *>(s_sbid + kSoloMax);   // [kSoloMax]
+    float *F_x1 = s_sinc + kSoloMax;                            // [3n] the cloud's points (bidder coordinates)
 
     const float *x1g = p.xyz1 + (size_t)cloud * n * 3;
     const float *x2g = p.xyz2 + (size_t)cloud * n * 3;
@@ -122,8 +232,10 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         ass_inv[k] = (p.assignment_inv && !p.fresh) ? p.assignment_inv[cb + base + k] : -1;
         assign[k] = p.fresh ? -1 : p.assignment[cb + base + k];
     }
+    if (p.solo && tid < 2) s_cnt[tid] = 0;
     cluster.sync();
 
+    int solo_from = -1;
     for (int it = 0; it < p.iters; ++it) {
         const bool last = (it == p.iters - 1);
         // ---- 1. compact the unassigned points homed here (order is result-neutral, emd_cuda.cu:85-93)
@@ -158,86 +270,9 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             const int jl = valid ? list[a] : 0;
             const int j = base + jl;
             const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
-            Top2 r;
-            r.best = kNegInit; r.better = kNegInit; r.idx = -1;
-            // Scan with deferred value evaluation.  A pair can change the top two only if v > better, i.e.
-            // sqrt(s) < 3 - better - price <= 3 - better (prices are >= 0): pairs with s above R2 = (3 - better + 2e-6)^2, or
-            // above (3 - better - price[k] + slack)^2 once the object's price is looked at, are skipped exactly.  The survivors' values (IEEE sqrt + fp64 arithmetic, ~30 instructions) used to be evaluated
-            // inside the scan, where one surviving lane sends the whole warp down the long path (27-60 % of the iterations).
-            // Now a lane queues its survivors (in index order, so the strict '>' tie rule is unchanged) and the warp
-            // evaluates them together when some lane has two; `better` for the radius is then the second best of the whole
-            // bidder group inside the warp (a valid lower bound of the final second best), not only the lane's own.
             const int wl = tpb < 32 ? tpb : 32;
-            float R2 = 3.0e38f, Rg = 3.0e38f;   // squared / plain pruning radius from the group's second best so far
-            int qn = 0, qk0 = 0, qk1 = 0;
-            float qs0 = 0.f, qs1 = 0.f;
-            auto evaluate = [&](int k, float s) {
-                const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
-                if (v > r.best) {
-                    r.better = r.best; r.best = v; r.idx = k;
-                } else if (v > r.better) {
-                    r.better = v;
-                }
-            };
-            auto flush = [&]() {   // warp-uniform
-                if (qn > 0) evaluate(qk0, qs0);
-                if (qn > 1) evaluate(qk1, qs1);
-                qn = 0;
-                float gb = r.best, g2 = r.better;   // group-wide (best, second best with multiplicity) so far
-                for (int o = wl >> 1; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, gb, o);
-                    const float o2 = __shfl_xor_sync(0xffffffffu, g2, o);
-                    g2 = fmaxf(fminf(gb, ob), fmaxf(g2, o2));
-                    gb = fmaxf(gb, ob);
-                }
-                Rg = 3.0f - g2;
-                const float R = Rg + 2e-6f;
-                R2 = R * R * 1.000001f;
-            };
-            // n is a multiple of 1024 and tpb a power of two <= 1024: every lane of the warp runs n / tpb iterations
-            auto consider = [&](int k, float s, bool pass) {   // warp-uniform call; `pass` = survived the price-free test
-                if (pass) {
-                    // per-object test with the object's own price: v > better needs sqrt(s) < 3 - better - price[k].  The
-                    // slack covers the fp32 rounding of this test and of the reference's value (|terms| are O(1): 3 ulp(4)).
-                    const float pk = price[k];
-                    const float Rk = (Rg - pk) + (4e-6f + 1e-6f * (fabsf(Rg) + fabsf(pk)));
-                    if (Rk > 0.f && s <= Rk * Rk * 1.000002f) {
-                        if (qn == 0) { qk0 = k; qs0 = s; } else { qk1 = k; qs1 = s; }
-                        ++qn;
-                    }
-                }
-                if (__any_sync(0xffffffffu, qn == 2)) flush();
-            };
-            if (((n / tpb) & 3) == 0) {
-                // four objects per lane and step: 12 shared-memory loads in flight, one vote for the common all-skipped case
-                const int st = tpb;
-                for (int k = t; k < n; k += 4 * st) {
-                    const float s0 = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-                    const float s1 = sqdist_exact(ox[k + st] - x1, oy[k + st] - y1, oz[k + st] - z1);
-                    const float s2 = sqdist_exact(ox[k + 2 * st] - x1, oy[k + 2 * st] - y1, oz[k + 2 * st] - z1);
-                    const float s3 = sqdist_exact(ox[k + 3 * st] - x1, oy[k + 3 * st] - y1, oz[k + 3 * st] - z1);
-                    const bool p0 = valid && s0 <= R2, p1 = valid && s1 <= R2, p2 = valid && s2 <= R2, p3 = valid && s3 <= R2;
-                    if (__any_sync(0xffffffffu, p0 || p1 || p2 || p3)) {
-                        consider(k, s0, p0);
-                        consider(k + st, s1, p1);
-                        consider(k + 2 * st, s2, p2);
-                        consider(k + 3 * st, s3, p3);
-                    }
-                }
-            } else {
-                for (int k = t; k < n; k += tpb) {
-                    const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-                    consider(k, s, valid && s <= R2);
-                }
-            }
-            flush();
-            // merge inside the warp over min(tpb,32) lanes
-            for (int o = wl >> 1; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, r.best, o);
-                const float o2 = __shfl_xor_sync(0xffffffffu, r.better, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, r.idx, o);
-                merge_top2(r, ob, o2, oi);
-            }
+            Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
+            warp_merge_top2(r, wl);
             if (tpb > 32) {  // bidder groups span several warps: finish through shared memory
                 __syncthreads();
                 if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }
@@ -301,6 +336,122 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
         }
         cluster.sync();  // [C]
+        // The number of unassigned points never grows (a winner takes one point off the list and evicts at most one), so once
+        // a cloud is down to a handful of bidders it stays there -- typically for hundreds of iterations at the training
+        // setting (eps = 0.05, 3000 iterations).  Those iterations are pure latency in the cluster-wide form (three cluster
+        // barriers, remote atomics, a 1024-thread scan for one bidder): rank 0 finishes them alone.
+        if (p.solo && total_u <= kSoloMax && !last) { solo_from = it + 1; break; }
+    }
+
+    if (solo_from >= 0) {
+        {   // gather the sliced state and the unassigned points in rank 0
+            float *r_maxinc = cluster.map_shared_rank(F_maxinc, 0);
+            int *r_winner = cluster.map_shared_rank(F_winner, 0), *r_inv = cluster.map_shared_rank(F_inv, 0);
+            int *r_assign = cluster.map_shared_rank(F_assign, 0), *r_bid = cluster.map_shared_rank(F_bid, 0);
+            float *r_binc = cluster.map_shared_rank(F_binc, 0);
+            int *r_list = cluster.map_shared_rank(s_list, 0), *r_cnt = cluster.map_shared_rank(s_cnt, 0);
+            for (int k = tid; k < ns; k += kEmdThreads) {
+                r_maxinc[base + k] = max_inc[k]; r_winner[base + k] = winner[k]; r_inv[base + k] = ass_inv[k];
+                r_assign[base + k] = assign[k]; r_bid[base + k] = bid[k]; r_binc[base + k] = bid_inc[k];
+                if (assign[k] == -1) {
+                    const int pos = atomicAdd(r_cnt, 1);
+                    if (pos < kSoloMax) r_list[pos] = base + k;
+                }
+            }
+        }
+        cluster.sync();
+        if (rank == 0) {
+            for (int i = tid; i < 3 * n; i += kEmdThreads) F_x1[i] = x1g[i];
+            __syncthreads();
+            int cur = 0;
+            for (int it = solo_from; it < p.iters; ++it) {
+                const bool last = (it == p.iters - 1);
+                const int u = min(s_cnt[cur], kSoloMax);
+                if (u == 0) break;
+                int *lst = s_list + cur * kSoloMax, *nxt = s_list + (cur ^ 1) * kSoloMax;
+                if (tid == 0) s_cnt[cur ^ 1] = 0;
+                // Bid: all u bidders in one pass, 1024 / G threads each (G = next power of two >= u, so >= 32 threads)
+                {
+                    int G = 1;
+                    while (G < u) G <<= 1;
+                    const int tpb = kEmdThreads / G, wpb = tpb >> 5;
+                    const int g = tid / tpb, t = tid - g * tpb;
+                    const bool valid = g < u;
+                    const int j = lst[valid ? g : 0];
+                    const float x1 = F_x1[j * 3 + 0], y1 = F_x1[j * 3 + 1], z1 = F_x1[j * 3 + 2];
+                    Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
+                    warp_merge_top2(r, 32);
+                    if (wpb > 1) {   // the group's warps meet in shared memory; its first warp merges them with a shuffle tree
+                        if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }
+                        __syncthreads();
+                        if (t < 32) {
+                            const bool have = lane < wpb;
+                            r.best = have ? w_best[warp + lane] : kNegInit;
+                            r.better = have ? w_better[warp + lane] : kNegInit;
+                            r.idx = have ? w_idx[warp + lane] : -1;
+                            warp_merge_top2(r, wpb);
+                        }
+                    }
+                    if (valid && t == 0) {
+                        const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
+                        F_bid[j] = r.idx; F_binc[j] = inc;
+                        s_sbid[g] = r.idx; s_sinc[g] = inc;
+                        if (r.idx >= 0) atomic_max_float(F_maxinc + r.idx, inc);
+                    }
+                }
+                __syncthreads();
+                // GetMax
+                if (tid < u) {
+                    const int o = s_sbid[tid];
+                    if (o >= 0) {
+                        const double bi = (double)s_sinc[tid], mi = (double)F_maxinc[o];
+                        if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMin(F_winner + o, lst[tid]);
+                    }
+                }
+                __syncthreads();
+                // Assign; whoever stays or becomes unassigned goes on the next list
+                if (tid < u) {
+                    const int j = lst[tid], o = s_sbid[tid];
+                    int push = j;
+                    if (o >= 0) {
+                        const int w = F_winner[o];
+                        if (last || w == j) {
+                            const float inc = s_sinc[tid];
+                            const int old = F_inv[o];
+                            push = -1;
+                            if (!last && old != -1) { F_assign[old] = -1; push = old; }
+                            F_inv[o] = j;
+                            F_assign[j] = o;
+                            price[o] = __fadd_rn(price[o], inc);
+                            F_maxinc[o] = kNegInit;
+                            F_winner[o] = INT_MAX;
+                        }
+                    }
+                    if (push >= 0) {
+                        const int pos = atomicAdd(s_cnt + (cur ^ 1), 1);
+                        if (pos < kSoloMax) nxt[pos] = push;
+                    }
+                }
+                __syncthreads();
+                cur ^= 1;
+            }
+            // CalcDist + write-back for the whole cloud
+            for (int j = tid; j < n; j += kEmdThreads) {
+                const int o = F_assign[j];
+                float d = 0.f;
+                if (o >= 0)
+                    d = sqdist_exact(x1g[j * 3 + 0] - ox[o], x1g[j * 3 + 1] - oy[o], x1g[j * 3 + 2] - oz[o]);
+                p.dist[cb + j] = d;
+                p.assignment[cb + j] = o;
+                if (p.assignment_inv) p.assignment_inv[cb + j] = F_inv[j];
+                if (p.max_increments) p.max_increments[cb + j] = F_maxinc[j];
+                if (p.bid) p.bid[cb + j] = F_bid[j];
+                if (p.bid_increments) p.bid_increments[cb + j] = F_binc[j];
+                if (p.price) p.price[cb + j] = price[j];
+            }
+        }
+        cluster.sync();  // keep every CTA's shared memory alive until rank 0 is done
+        return;
     }
 
     // ---- CalcDist (emd_cuda.cu:217-226) + write-back of the state the reference leaves in its tensors
@@ -342,10 +493,14 @@ static size_t emd_smem_bytes(int n, int S) {
     const int ns = n / S;
     return sizeof(float) * (size_t)(4 * n) + sizeof(float) * (size_t)(7 * ns) + sizeof(float) * (32 * 3 + 8 + 4);
 }
+static size_t emd_solo_bytes(int n) { return sizeof(float) * ((size_t)9 * n + 2 * kSoloMax + 2 + 2 * kSoloMax); }
 
 }  // namespace psd
 
 using namespace psd;
+
+static int g_emd_solo = 1;
+int psd_set_emd_solo(int enable) { const int old = g_emd_solo; if (enable == 0 || enable == 1) g_emd_solo = enable; return old; }
 
 // returns cudaSuccess, or an error; *unsupported is set when the shape does not fit the persistent kernel
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
@@ -366,13 +521,15 @@ cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, 
     }
     while (S < 8 && emd_smem_bytes(n, S) > (size_t)max_smem) S *= 2;
     if (emd_smem_bytes(n, S) > (size_t)max_smem || (n % S) != 0) { *unsupported = 1; return cudaSuccess; }
-    const size_t smem = emd_smem_bytes(n, S);
+    size_t smem = emd_smem_bytes(n, S);
+    const int solo = (smem + emd_solo_bytes(n) <= (size_t)max_smem && g_emd_solo) ? 1 : 0;
+    if (solo) smem += emd_solo_bytes(n);
     cudaError_t e = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     EmdParams p;
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.dist = dist; p.assignment = assignment; p.price = price;
     p.assignment_inv = assignment_inv; p.max_increments = max_increments; p.bid = bid; p.bid_increments = bid_increments;
-    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh;
+    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = solo;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned int)(b * S));
     cfg.blockDim = dim3(kEmdThreads);

@@ -211,6 +211,11 @@ int psd_chamfer_stats(long long *out_host2, int reset);
  * 3 = tensor-core (tcgen05) kernel.  All produce identical results.  Returns the previous setting. */
 int psd_chamfer_nn_variant(int variant);
 
+/* Test / profiling switch of the auction kernel's solo mode (once a cloud is down to <= 32 unassigned points, one CTA of its
+ * cluster finishes the auction alone, one warp per bidder, without cluster barriers; results are identical).  enable: 0 / 1
+ * sets it, anything else only queries; returns the previous setting.  Default 1. */
+int psd_emd_solo_mode(int enable);
+
 /* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
  * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a
  * unit is a block of 128 queries in launch order (direction 1 blocks first).  dump_ld >= n and m rounded up to 128. */

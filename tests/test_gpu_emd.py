@@ -39,6 +39,34 @@ def test_emd_bit_exact_all_cluster_sizes(pkg, oracle, cuda, cluster, cfg):
         pass
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("cfg", [("uniform", 3, 1024, 0.05, 3000), ("clustered", 2, 2048, 0.05, 3000), ("uniform", 2, 1024, 0.05, 150),
+                                 ("uniform", 2, 1024, 0.05, 60), ("uniform", 1, 4096, 0.05, 500), ("dup", 2, 1024, 0.05, 3000)])
+def test_emd_solo_mode_training_setting(pkg, oracle, cuda, cluster, cfg):
+    """The training setting (loss/loss.py:18-28: eps 0.05, 3000 iterations) spends most iterations with a handful of
+    bidders; below 33 of them one CTA finishes the auction alone (solo mode).  Same bits as the oracle and as the
+    cluster-wide form, also when the run ends (forced assignment) inside the solo phase."""
+    kind, b, n, eps, iters = cfg
+    x, y = make_clouds(kind, b, n, n, seed=7 + n + iters)
+    wd, wa, state = oracle.emd_forward(x, y, eps, iters, nthreads=8, full_state=True)
+    lib = pkg._lib.lib
+    res = {}
+    for solo in (1, 0):
+        old = lib.psd_emd_solo_mode(solo)
+        try:
+            res[solo] = run_cluster(pkg, cuda, x, y, eps, iters, cluster)
+        finally:
+            lib.psd_emd_solo_mode(old)
+        dist, ass, price, inv = res[solo]
+        assert (ass == wa).all(), f"solo={solo}: assignment differs in {(ass != wa).sum()} places"
+        assert (dist.view(np.uint32) == wd.view(np.uint32)).all()
+    if iters == 3000:   # converged long before the last iteration: no forced assignment, the scratch state is deterministic
+        for k in (2, 3):
+            assert (res[1][k].view(np.uint32) == res[0][k].view(np.uint32)).all()
+        assert (res[1][2].view(np.uint32) == state["price"].view(np.uint32)).all()
+        assert (res[1][3] == state["assignment_inv"]).all()
+
+
 def test_emd_module_config3_and_backward(pkg, oracle, cuda):
     """BASELINE.json configs[2]: B=32, n=2048, eps=0.005, iters=50 through emdModule, plus the gradient."""
     x, y = make_clouds("uniform", 32, 2048, 2048, seed=0)

@@ -138,6 +138,18 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         }
         if (__any_sync(0xffffffffu, qn == 2)) flush();
     };
+    if (n <= 8 * tpb) {
+        // A handful of objects per thread (few bidders, many threads each): the queue / vote / radius machinery is a long
+        // dependent chain here and prunes nothing (the radius is unknown until the first evaluation), so every object's
+        // value is evaluated directly; the independent sqrt / fp64 chains of a thread's objects overlap.
+#pragma unroll 4
+        for (int k = t; k < n; k += tpb) {
+            const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+            const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
+            if (valid) apply(k, v);
+        }
+        return r;
+    }
     if (((n / tpb) & 3) == 0) {
         // four objects per lane and step: 12 shared-memory loads in flight, one vote for the common all-skipped case
         const int st = tpb;

@@ -409,6 +409,14 @@ def main():
             emd_ms = min(event_time_ms(torch, lambda: pkg.emd.forward_fresh(ex, ey, edist, eass, EMD_EPS, EMD_ITERS)) for _ in range(5))
             out["emd"] = {"clouds_per_s": B / (emd_ms * 1e-3), "ms": emd_ms, "config": f"B={B} n={N} eps={EMD_EPS} iters={EMD_ITERS}",
                           "launches": 1}
+            # the training setting of the same op (loss/loss.py:18-28: eps=0.05, iters=3000, generator output n=1024)
+            tx_, ty_ = ex[:, :1024].contiguous(), ey[:, :1024].contiguous()
+            tdist = torch.empty(B, 1024, device=dev); tass = torch.empty(B, 1024, device=dev, dtype=torch.int32)
+            pkg.emd.forward_fresh(tx_, ty_, tdist, tass, 0.05, 3000)
+            torch.cuda.synchronize()
+            emd_train_ms = min(event_time_ms(torch, lambda: pkg.emd.forward_fresh(tx_, ty_, tdist, tass, 0.05, 3000)) for _ in range(3))
+            out["emd_train"] = {"clouds_per_s": B / (emd_train_ms * 1e-3), "ms": emd_train_ms,
+                                "config": f"B={B} n=1024 eps=0.05 iters=3000 (Loss.get_emd_loss)", "launches": 1}
             # ---- the reference's CUDA extensions on the same GPU (oracle/_ref, built unmodified)
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "ref_chamfer_3D"))
@@ -435,8 +443,16 @@ def main():
                     ref_emd.forward(ex, ey, *a, EMD_EPS, EMD_ITERS)
                 ref_emd_step(); torch.cuda.synchronize()
                 rems = min(event_time_ms(torch, ref_emd_step) for _ in range(3))
+                def ref_emd_train_step():
+                    n1 = 1024
+                    a = [z(B, n1), z(B, n1, dt=torch.int32) - 1, z(B, n1), z(B, n1, dt=torch.int32) - 1, z(B, n1, dt=torch.int32), z(B, n1), z(B, n1),
+                         z(B * n1, dt=torch.int32), z(512, dt=torch.int32), z(512, dt=torch.int32), z(512, dt=torch.int32), z(B * n1, dt=torch.int32)]
+                    ref_emd.forward(tx_, ty_, *a, 0.05, 3000)
+                ref_emd_train_step(); torch.cuda.synchronize()
+                retms = event_time_ms(torch, ref_emd_train_step)
                 out["reference_cuda"] = {"chamfer_fwd_bwd_pairs_per_s": pairs_step / (rms * 1e-3), "chamfer_ms_per_step": rms,
                                          "emd_clouds_per_s": B / (rems * 1e-3), "emd_ms": rems,
+                                         "emd_train_clouds_per_s": B / (retms * 1e-3), "emd_train_ms": retms,
                                          "what": "reference chamfer3D/emd extensions compiled unmodified for sm_100a (oracle/_ref), same GPU, default stream, CUDA events"}
             except Exception as e:  # noqa: BLE001
                 out["reference_cuda"] = {"unavailable": repr(e)[:200]}

@@ -78,6 +78,30 @@ __device__ __forceinline__ void merge_top2(Top2 &a, float ob, float o2, int oi) 
     }
 }
 
+// monotone map float -> uint32 (no NaN, no -0 among the values it is used for)
+__device__ __forceinline__ unsigned int ford(float v) {
+    const unsigned int u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float funord(unsigned int o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// Full-warp merge of 32 partial (best, second best with multiplicity, lowest index of best) results with redux.sync:
+// best = max; index = lowest among the lanes holding the max; second best = the max again if two lanes hold it, else the
+// largest of (holder's own second best, everybody else's best).  Same function of the multiset as a chain of merge_top2.
+__device__ __forceinline__ void warp_top2_redux(Top2 &r) {
+    const unsigned int ob = ford(r.best);
+    const unsigned int m1 = __reduce_max_sync(0xffffffffu, ob);
+    const bool holder = ob == m1;
+    const int nh = __popc(__ballot_sync(0xffffffffu, holder));
+    const unsigned int idx = __reduce_min_sync(0xffffffffu, holder ? (unsigned int)r.idx : 0xffffffffu);
+    const unsigned int second = __reduce_max_sync(0xffffffffu, ford(holder ? r.better : r.best));
+    r.best = funord(m1);
+    r.idx = (int)idx;
+    r.better = nh >= 2 ? r.best : funord(second);
+}
+
 // One bidder group's scan of all n objects: thread t of tpb (a power of two) looks at objects t, t + tpb, ... and returns its
 // partial (best, second best, index of best); the caller merges the group.
 // Scan with deferred value evaluation.  A pair can change the top two only if v > better, i.e.
@@ -138,15 +162,50 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         }
         if (__any_sync(0xffffffffu, qn == 2)) flush();
     };
-    if (n <= 8 * tpb) {
-        // A handful of objects per thread (few bidders, many threads each): the queue / vote / radius machinery is a long
-        // dependent chain here and prunes nothing (the radius is unknown until the first evaluation), so every object's
-        // value is evaluated directly; the independent sqrt / fp64 chains of a thread's objects overlap.
-#pragma unroll 4
-        for (int k = t; k < n; k += tpb) {
-            const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-            const float v = (float)(3.0 - (double)__fsqrt_rn(s) - (double)price[k]);
-            if (valid) apply(k, v);
+    if (n <= 4 * tpb) {
+        // A handful of objects per thread (few bidders, many threads each; a warp belongs to one bidder).  The queue / vote
+        // / radius machinery is a long dependent chain here and prunes nothing, and evaluating every value exactly is bound
+        // by the fp32<->fp64 conversions (16 lanes per clock).  So: an fp32 estimate a = (3 - sqrt(s)) - price of every
+        // value with an error bound delta, the warp's second best LOWER bound g2 (at least two objects have an exact value
+        // >= g2, so the group's final second best is >= g2), and the exact evaluation only of objects whose UPPER bound
+        // reaches g2 -- nothing else can enter the top two.  Candidates are applied in index order.
+        {
+            const int k0 = t;   // n / tpb is 1, 2 or 4
+            float au[4], sv[4];            // upper bounds of the values, squared distances
+            float a1 = kNegInit, a2 = kNegInit;   // this thread's two largest LOWER bounds
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + i * tpb;
+                au[i] = kNegInit; sv[i] = 0.f;
+                if (k < n && valid) {
+                    sv[i] = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+                    const float pk = price[k];
+                    float d;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(sv[i]));   // relative error <= 2^-23
+                    const float a = (3.0f - d) - pk;
+                    // |a - v| <= 2^-23 d + ulp(3 - d)/2 + ulp(a) <= 3.6e-7 (3 + d + |pk|)
+                    const float delta = 1e-6f * (3.0f + d + fabsf(pk));
+                    const float al = a - delta;
+                    au[i] = a + delta;
+                    a2 = fmaxf(a2, fminf(a1, al));
+                    a1 = fmaxf(a1, al);
+                }
+            }
+            // warp-wide second best (with multiplicity) of the lower bounds: the group's final second best is at least this
+            const unsigned int o1 = ford(a1);
+            const unsigned int m1 = __reduce_max_sync(0xffffffffu, o1);
+            const bool holder = o1 == m1;
+            const int nh = __popc(__ballot_sync(0xffffffffu, holder));
+            const float g2 = nh >= 2 ? funord(m1) : funord(__reduce_max_sync(0xffffffffu, ford(holder ? a2 : a1)));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + i * tpb;
+                const bool cand = k < n && valid && au[i] >= g2;
+                if (__any_sync(0xffffffffu, cand)) {
+                    const float v = (float)(3.0 - (double)__fsqrt_rn(sv[i]) - (double)price[cand ? k : 0]);
+                    if (cand) apply(k, v);
+                }
+            }
         }
         return r;
     }
@@ -384,16 +443,15 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 if (tid == 0) s_cnt[cur ^ 1] = 0;
                 // Bid: all u bidders in one pass, 1024 / G threads each (G = next power of two >= u, so >= 32 threads)
                 {
-                    int G = 1;
-                    while (G < u) G <<= 1;
-                    const int tpb = kEmdThreads / G, wpb = tpb >> 5;
-                    const int g = tid / tpb, t = tid - g * tpb;
+                    const int lg = u <= 1 ? 0 : 32 - __clz(u - 1);          // log2(G)
+                    const int tpb = kEmdThreads >> lg, wpb = tpb >> 5;
+                    const int g = tid >> (10 - lg), t = tid & (tpb - 1);
                     const bool valid = g < u;
                     const int j = lst[valid ? g : 0];
                     const float x1 = F_x1[j * 3 + 0], y1 = F_x1[j * 3 + 1], z1 = F_x1[j * 3 + 2];
                     Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
-                    warp_merge_top2(r, 32);
-                    if (wpb > 1) {   // the group's warps meet in shared memory; its first warp merges them with a shuffle tree
+                    warp_top2_redux(r);
+                    if (wpb > 1) {   // the group's warps meet in shared memory; its first warp merges them
                         if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }
                         __syncthreads();
                         if (t < 32) {
@@ -401,7 +459,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                             r.best = have ? w_best[warp + lane] : kNegInit;
                             r.better = have ? w_better[warp + lane] : kNegInit;
                             r.idx = have ? w_idx[warp + lane] : -1;
-                            warp_merge_top2(r, wpb);
+                            warp_top2_redux(r);
                         }
                     }
                     if (valid && t == 0) {

@@ -118,21 +118,34 @@ def run_reference_arm(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    bs = 4  # bounded sample: 4 of the 32 clouds per step
     torch.manual_seed(0)
-    x = torch.rand(bs, N, 3)
-    y = torch.rand(bs, M, 3)
+    xa = torch.rand(4, N, 3)
+    ya = torch.rand(4, M, 3)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
 
-    def step():
-        a = x.clone().requires_grad_(True)
-        b = y.clone().requires_grad_(True)
-        P = O.torch_batched_pairwise_dist(a, b)
-        loss = torch.min(P, 2)[0].float().mean() + torch.min(P, 1)[0].float().mean()
-        loss.backward()
-        return float(loss)
+    def make_step(bs):
+        x, y = xa[:bs], ya[:bs]
 
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
+        def step():
+            a = x.clone().requires_grad_(True)
+            b = y.clone().requires_grad_(True)
+            P = O.torch_batched_pairwise_dist(a, b)
+            loss = torch.min(P, 2)[0].float().mean() + torch.min(P, 1)[0].float().mean()
+            loss.backward()
+            return float(loss)
+        return step
+
+    # bounded sample: 4, 2 or 1 of the 32 clouds per step, sized so that the K + W steps asked for end within ~2.5 minutes
+    bs = 4
+    step = make_step(bs)
+    step()
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    while bs > 1 and t1 * (steps + warm) > 150.0:
+        bs //= 2
+        t1 *= 0.5
+    step = make_step(bs)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -142,7 +155,7 @@ def run_reference_arm(args):
     pairs = 2.0 * bs * N * M
     v = pairs / dt
     sample = f"{bs} of {B} clouds per step (N=M={N}), {steps} steps, torch fp64 xx+yy-2*bmm + autograd backward"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -150,7 +163,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # --------------------------------------------------------------------------------------------------
@@ -164,8 +177,29 @@ def event_time_ms(torch, fn, stream=None):
     return e0.elapsed_time(e1)
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else a library prints there (NCCL's version banner, for
+    one) is sent to stderr instead.  The JSON line goes to the saved descriptor through emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -474,7 +508,7 @@ def main():
                                        "sample": f"{bs} of {B} clouds (N=M={N}) fwd+bwd x{reps_c}, oracle/psd_oracle.c with OpenMP over clouds"}
             except Exception as e:  # noqa: BLE001
                 out["cpu_baseline"] = {"unavailable": repr(e)[:200]}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -592,7 +592,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         };
         // stage, part 2: build the operands of unit ul in shared memory and signal the MMA warp.
         auto stage_finish = [&](int ul, const Unit &u) {
-            const NNDirection &D = p.dir[u.d];
             if (need_b) {
                 cp_async_wait_all();
                 help_bar();   // every helper's raw targets have landed

@@ -359,6 +359,24 @@ def main():
     e2e_value = world * pairs_step * Ke / (float(te[0].item()) * 1e-3)
     e2e_sync_value = world * pairs_step * Ke / (float(te[1].item()) * 1e-3)
 
+    # ---- EMD (BASELINE configs[2]) on every GPU of the job: each rank its own B clouds (weak scaling), max over ranks
+    emd_all = None
+    if not args.no_extras:
+        ex_, ey_ = xs[0], ys[0]
+        ed_ = torch.empty(B, N, device=dev); ea_ = torch.empty(B, N, device=dev, dtype=torch.int32)
+        for _ in range(2):
+            pkg.emd.forward_fresh(ex_, ey_, ed_, ea_, EMD_EPS, EMD_ITERS)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        reps_e = 10
+        ems = event_time_ms(torch, lambda: [pkg.emd.forward_fresh(ex_, ey_, ed_, ea_, EMD_EPS, EMD_ITERS) for _ in range(reps_e)]) / reps_e
+        tm = torch.tensor([ems], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        emd_all = {"clouds_per_s": world * B / (float(tm.item()) * 1e-3), "ms": float(tm.item()), "n_gpus": world,
+                   "config": f"B={B} per GPU, n={N}, eps={EMD_EPS}, iters={EMD_ITERS}; {reps_e} back-to-back launches, max over ranks"}
+
     out = {
         "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -375,6 +393,8 @@ def main():
         "gpu_launches": 2 * K,   # value leg: chamfer_nn_tc_kernel + chamfer_grad_kernel per step (e2e adds chamfer_mean_loss_kernel)
         "clocks": sampler.result(),
     }
+    if emd_all is not None:
+        out["emd_all_gpus"] = emd_all
 
     if rank == 0:
         # ---- roofline of the dominant kernel: chamfer_nn_kernel alone, back-to-back launches, CUDA events
@@ -442,7 +462,7 @@ def main():
             torch.cuda.synchronize()
             emd_ms = min(event_time_ms(torch, lambda: pkg.emd.forward_fresh(ex, ey, edist, eass, EMD_EPS, EMD_ITERS)) for _ in range(5))
             out["emd"] = {"clouds_per_s": B / (emd_ms * 1e-3), "ms": emd_ms, "config": f"B={B} n={N} eps={EMD_EPS} iters={EMD_ITERS}",
-                          "launches": 1}
+                          "launches": 1, "scope": "rank 0's GPU; emd_all_gpus is the whole job"}
             # the training setting of the same op (loss/loss.py:18-28: eps=0.05, iters=3000, generator output n=1024)
             tx_, ty_ = ex[:, :1024].contiguous(), ey[:, :1024].contiguous()
             tdist = torch.empty(B, 1024, device=dev); tass = torch.empty(B, 1024, device=dev, dtype=torch.int32)

@@ -1,4 +1,5 @@
-"""Small fixed workload for ncu: 3x chamfer forward, 3x backward, 1x EMD at BASELINE configs 2/3."""
+"""Small fixed workload for ncu: 3x chamfer forward, 3x backward, 1x EMD at BASELINE configs 2/3 (+ --emd-train: 1x EMD at the
+training setting)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -22,5 +23,9 @@ for _ in range(3):
     assert pkg.chamfer_3D.backward(x, y, gx1, gx2, g1, g2, i1, i2) == 1
 if "--no-emd" not in sys.argv:
     assert pkg.emd.forward_fresh(x, y, dist, ass, 0.005, 50) == 1
+if "--emd-train" in sys.argv:   # the training setting: eps 0.05, 3000 iterations, n = 1024 (solo mode for most iterations)
+    xt, yt = x[:, :1024].contiguous(), y[:, :1024].contiguous()
+    dt_, at_ = torch.empty(B, 1024, device=dev), torch.empty(B, 1024, device=dev, dtype=torch.int32)
+    assert pkg.emd.forward_fresh(xt, yt, dt_, at_, 0.05, 3000) == 1
 torch.cuda.synchronize()
 print("ok", float(d1.sum()), int(ass.sum()))

@@ -323,23 +323,41 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         __syncthreads();
         const int u = *cnt;
         if (tid < S) *cluster.map_shared_rank(ucount + rank, tid) = u;
+        // The bidders are homed by point index, so the CTAs of a cluster hold different numbers of them and the slowest one
+        // sets the pace of every iteration (cluster-barrier stalls were 26 % of the samples).  One more barrier makes the
+        // counts known before the scan, and every CTA takes an equal share of the cluster's bidder list: bidder ids are read
+        // from their home CTA's list over DSMEM, the results go back to the home CTA's bid / bid_increments.
+        if (S > 1) cluster.sync();  // [R] counts visible
+        int total_u = 0, lo = 0, hi = u;
+        if (S > 1) {
+            for (int r2 = 0; r2 < S; ++r2) total_u += ucount[r2];
+            lo = (int)(((long long)rank * total_u) / S);
+            hi = (int)(((long long)(rank + 1) * total_u) / S);
+        } else {
+            total_u = u;
+        }
+        if (total_u == 0) break;  // uniform across the cluster; later iterations cannot change anything
+        const int mine = hi - lo;
 
         // ---- 2./3. Bid (emd_cuda.cu:95-179): G bidders at a time, tpb threads per bidder
-        // The u bidders are processed in passes of G = a power of two bidders (tpb = 1024 / G threads each).  One pass of
-        // the next power of two >= u wastes up to half of the lanes and makes a CTA with u just above a power of two
-        // twice as slow as its cluster mates (they all wait at the cluster barrier): take that pass only if at least
-        // 3/4 of its groups are real, else a full pass of half the size and continue with the remainder.
-        for (int a0 = 0, G = 1; a0 < u; a0 += G) {
-            const int rem = u - a0;
+        // The bidders are processed in passes of G = a power of two bidders (tpb = 1024 / G threads each).  One pass of
+        // the next power of two >= mine wastes up to half of the lanes: take that pass only if at least 3/4 of its groups
+        // are real, else a full pass of half the size and continue with the remainder.
+        for (int a0 = 0, G = 1; a0 < mine; a0 += G) {
+            const int rem = mine - a0;
             G = 1;
             while (G < rem && G < kEmdThreads) G <<= 1;
             if (G > 1 && rem * 4 < G * 3) G >>= 1;
             const int tpb = kEmdThreads / G;
             const int g = tid / tpb, t = tid - g * tpb;
-            const int a = a0 + g;
-            const bool valid = a < u;
-            const int jl = valid ? list[a] : 0;
-            const int j = base + jl;
+            const bool valid = a0 + g < mine;
+            // global position in the cluster's bidder list -> (home rank, index in its list)
+            int a = lo + (valid ? a0 + g : 0), hr = 0;
+            if (S > 1) {
+                while (hr < S - 1 && a >= ucount[hr]) { a -= ucount[hr]; ++hr; }
+            }
+            const int jl = *(cluster.map_shared_rank(list, hr) + a);   // idle groups look at the first bidder of the share
+            const int j = hr * ns + jl;
             const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
             const int wl = tpb < 32 ? tpb : 32;
             Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
@@ -355,8 +373,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
             if (valid && t == 0) {
                 const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
-                bid[jl] = r.idx;
-                bid_inc[jl] = inc;
+                *(cluster.map_shared_rank(bid, hr) + jl) = r.idx;
+                *(cluster.map_shared_rank(bid_inc, hr) + jl) = inc;
                 if (r.idx >= 0) {
                     const int orank = r.idx / ns;
                     atomic_max_float(cluster.map_shared_rank(max_inc, orank) + (r.idx - orank * ns), inc);
@@ -364,10 +382,6 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
         }
         cluster.sync();  // [A] all bids and max_increments visible cluster-wide
-
-        int total_u = 0;
-        for (int r2 = 0; r2 < S; ++r2) total_u += ucount[r2];
-        if (total_u == 0) break;  // uniform across the cluster; later iterations cannot change anything
 
         // ---- 4. GetMax (emd_cuda.cu:181-194): lowest bidder index within +-1e-6 (fp64) of the maximum
         for (int a = tid; a < u; a += kEmdThreads) {

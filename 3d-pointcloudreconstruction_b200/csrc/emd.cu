@@ -210,19 +210,21 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         return r;
     }
     if (((n / tpb) & 3) == 0) {
-        // four objects per lane and step: 12 shared-memory loads in flight, one vote for the common all-skipped case
-        const int st = tpb;
-        for (int k = t; k < n; k += 4 * st) {
-            const float s0 = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-            const float s1 = sqdist_exact(ox[k + st] - x1, oy[k + st] - y1, oz[k + st] - z1);
-            const float s2 = sqdist_exact(ox[k + 2 * st] - x1, oy[k + 2 * st] - y1, oz[k + 2 * st] - z1);
-            const float s3 = sqdist_exact(ox[k + 3 * st] - x1, oy[k + 3 * st] - y1, oz[k + 3 * st] - z1);
+        // four CONSECUTIVE objects per lane and step (3 x LDS.128), one vote for the common all-skipped case; a lane still
+        // meets its objects in index order, and the group merge breaks ties by the lowest index
+        for (int k = 4 * t; k < n; k += 4 * tpb) {
+            const float4 xa = *reinterpret_cast<const float4 *>(ox + k), ya = *reinterpret_cast<const float4 *>(oy + k),
+                         za = *reinterpret_cast<const float4 *>(oz + k);
+            const float s0 = sqdist_exact(xa.x - x1, ya.x - y1, za.x - z1);
+            const float s1 = sqdist_exact(xa.y - x1, ya.y - y1, za.y - z1);
+            const float s2 = sqdist_exact(xa.z - x1, ya.z - y1, za.z - z1);
+            const float s3 = sqdist_exact(xa.w - x1, ya.w - y1, za.w - z1);
             const bool p0 = valid && s0 <= R2, p1 = valid && s1 <= R2, p2 = valid && s2 <= R2, p3 = valid && s3 <= R2;
             if (__any_sync(0xffffffffu, p0 || p1 || p2 || p3)) {
                 consider(k, s0, p0);
-                consider(k + st, s1, p1);
-                consider(k + 2 * st, s2, p2);
-                consider(k + 3 * st, s3, p3);
+                consider(k + 1, s1, p1);
+                consider(k + 2, s2, p2);
+                consider(k + 3, s3, p3);
             }
         }
     } else {

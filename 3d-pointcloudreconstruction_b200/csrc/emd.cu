@@ -478,6 +478,41 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                             warp_top2_redux(r);
                         }
                     }
+                    if (u == 1) {
+                        // a single bidder (the usual case in the long tail: an eviction chain): thread 0 runs winner
+                        // selection and assignment right here, with the state transitions of the general path
+                        if (tid == 0) {
+                            const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
+                            const int o = r.idx;
+                            F_bid[j] = o; F_binc[j] = inc;
+                            int push = j;
+                            if (o >= 0) {
+                                float mi = F_maxinc[o];
+                                if (inc > mi) mi = inc;                                   // atomic_max_float
+                                int w = F_winner[o];
+                                const double bi = (double)inc, md = (double)mi;
+                                if (bi - 1e-6 <= md && md <= bi + 1e-6 && j < w) w = j;     // GetMax
+                                if (last || w == j) {                                      // Assign
+                                    const int old = F_inv[o];
+                                    push = -1;
+                                    if (!last && old != -1) { F_assign[old] = -1; push = old; }
+                                    F_inv[o] = j;
+                                    F_assign[j] = o;
+                                    price[o] = __fadd_rn(price[o], inc);
+                                    F_maxinc[o] = kNegInit;
+                                    F_winner[o] = INT_MAX;
+                                } else {
+                                    F_maxinc[o] = mi;
+                                    F_winner[o] = w;
+                                }
+                            }
+                            s_cnt[cur ^ 1] = push >= 0 ? 1 : 0;
+                            if (push >= 0) nxt[0] = push;
+                        }
+                        __syncthreads();
+                        cur ^= 1;
+                        continue;
+                    }
                     if (valid && t == 0) {
                         const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
                         F_bid[j] = r.idx; F_binc[j] = inc;

@@ -211,10 +211,16 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
     }
     if (((n / tpb) & 3) == 0) {
         // four CONSECUTIVE objects per lane and step (3 x LDS.128), one vote for the common all-skipped case; a lane still
-        // meets its objects in index order, and the group merge breaks ties by the lowest index
+        // meets its objects in index order, and the group merge breaks ties by the lowest index.  The coordinates never
+        // change after the prologue, so they are read through explicit shared-space addresses (no generic -> shared window
+        // arithmetic in the loop).
+        const unsigned int sx = (unsigned int)__cvta_generic_to_shared(ox), sy = (unsigned int)__cvta_generic_to_shared(oy),
+                           sz = (unsigned int)__cvta_generic_to_shared(oz);
         for (int k = 4 * t; k < n; k += 4 * tpb) {
-            const float4 xa = *reinterpret_cast<const float4 *>(ox + k), ya = *reinterpret_cast<const float4 *>(oy + k),
-                         za = *reinterpret_cast<const float4 *>(oz + k);
+            float4 xa, ya, za;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
             const float s0 = sqdist_exact(xa.x - x1, ya.x - y1, za.x - z1);
             const float s1 = sqdist_exact(xa.y - x1, ya.y - y1, za.y - z1);
             const float s2 = sqdist_exact(xa.z - x1, ya.z - y1, za.z - z1);

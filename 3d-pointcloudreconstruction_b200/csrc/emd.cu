@@ -23,6 +23,7 @@
 // (best, better) only if v > better, which requires sqrt(s) < 3 - better + 2e-6 (prices are >= 0).
 #include <cooperative_groups.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "psd_common.cuh"
 
@@ -32,6 +33,8 @@ namespace psd {
 
 constexpr int kEmdThreads = 1024;
 constexpr float kNegInit = -1e9f;
+constexpr int kGridG = 8;                      // cells per axis of the object grid
+constexpr int kGridCells = kGridG * kGridG * kGridG;
 constexpr int kSoloMax = 32;   // bidders per cloud at or below which one CTA finishes the auction alone (one warp per bidder)
 
 struct EmdParams {
@@ -48,10 +51,18 @@ struct EmdParams {
     int iters;
     int fresh;  // 1: ignore the caller's state tensors and start from assignment = -1, price = 0
     int solo;   // 1: shared memory holds the solo-mode arrays (see emd_auction_kernel)
+    int grid;   // 1: shared memory holds the object grid (cell-sorted copy of the objects)
+    int grid_min_u;   // iterations with fewer bidders in the cluster use the full scan (a bidder per warp is latency bound)
 };
 
 // float atomicMax with the reference's semantics (emd_cuda.cu:10-20): CAS loop, `val > old` in float.
 __device__ __forceinline__ void atomic_max_float(float *address, float val) {
+    if (val >= 0.f) {
+        // a non-negative float is larger than another float exactly when its bit pattern is larger as a signed int (negative
+        // floats have the sign bit set): one fire-and-forget integer max, same final value as the CAS loop
+        atomicMax(reinterpret_cast<int *>(address), __float_as_int(val));
+        return;
+    }
     int ret = __float_as_int(*reinterpret_cast<volatile float *>(address));
     while (val > __int_as_float(ret)) {
         const int old = ret;
@@ -281,8 +292,19 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     int *w_idx = reinterpret_cast<int *>(w_better + 32);
     int *ucount = w_idx + 32;                                   // [8] bidder count of every rank
     int *cnt = ucount + 8;                                      // [1]
+    // object grid: the objects sorted by cell of a kGridG^3 grid over their bounding box
+    float *gx = reinterpret_cast<float *>(cnt + 4);             // [n] cell-sorted coordinates
+    float *gy = gx + n;
+    float *gz = gy + n;
+    int *gperm = reinterpret_cast<int *>(gz + n);               // [n] original object index
+    int *cell_start = gperm + n;                                // [kGridCells + 4]
+    int *cell_fill = cell_start + kGridCells + 4;               // [kGridCells]
+    float *gbox = reinterpret_cast<float *>(cell_fill + kGridCells);   // [8] min xyz, inverse cell size xyz, hmin, abs slack
+    unsigned int *gred = reinterpret_cast<unsigned int *>(gbox + 8);    // [8] min / max reduction (ordered uints), ok flag
+    int *gruns = reinterpret_cast<int *>(gred + 8);                      // [32 warps][2][32] run begin / prefix of run lengths
+    float *after_grid = p.grid ? reinterpret_cast<float *>(gruns + 32 * 64) : reinterpret_cast<float *>(cnt + 4);
     // solo mode (only rank 0's copies are used): the whole cloud's sliced state gathered into full-length arrays
-    float *F_maxinc = reinterpret_cast<float *>(cnt + 4);       // [n]
+    float *F_maxinc = after_grid;                               // [n]
     int *F_winner = reinterpret_cast<int *>(F_maxinc + n);      // [n]
     int *F_inv = F_winner + n;                                  // [n]
     int *F_assign = F_inv + n;                                  // [n]
@@ -312,6 +334,88 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         assign[k] = p.fresh ? -1 : p.assignment[cb + base + k];
     }
     if (p.solo && tid < 2) s_cnt[tid] = 0;
+    // ---- object grid (every CTA builds its own copy).  A bidder then visits the cells around it ring by ring and stops
+    // as soon as everything closer than its pruning radius has been seen, instead of testing all n objects.
+    bool use_grid = false;
+    if (p.grid) {
+        if (tid < 8) gred[tid] = (tid < 3) ? 0xffffffffu : 0u;
+        for (int c = tid; c < kGridCells; c += kEmdThreads) cell_fill[c] = 0;
+        __syncthreads();
+        {
+            unsigned int mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+            unsigned int bad = 0;
+            for (int k = tid; k < n; k += kEmdThreads) {
+                const float c3[3] = {ox[k], oy[k], oz[k]};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    bad |= !(fabsf(c3[a]) < 1e18f);
+                    const unsigned int o = ford(c3[a]);
+                    mn[a] = min(mn[a], o); mx[a] = max(mx[a], o);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = __reduce_min_sync(0xffffffffu, mn[a]);
+                mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
+            }
+            bad = __reduce_max_sync(0xffffffffu, bad);
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { atomicMin(gred + a, mn[a]); atomicMax(gred + 3 + a, mx[a]); }
+                if (bad) atomicMax(gred + 6, 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float hmin = 3.0e38f, slack = 0.f;
+            for (int a = 0; a < 3; ++a) {
+                const float lo3 = funord(gred[a]), hi3 = funord(gred[3 + a]);
+                const float h = (hi3 - lo3) / (float)kGridG;
+                gbox[a] = lo3;
+                gbox[3 + a] = h > 0.f ? 1.0f / h : 0.f;
+                hmin = fminf(hmin, h);
+                slack += fabsf(lo3) + fabsf(hi3);
+            }
+            gbox[6] = hmin;
+            gbox[7] = 2e-6f * slack + 1e-30f;   // cell assignment of objects and bidders is exact up to a few ulps of the coordinates
+        }
+        __syncthreads();
+        use_grid = gred[6] == 0u && gbox[6] > 0.f;
+        if (use_grid) {
+            auto cell_of = [&](float x, float y, float z) {
+                const int cx = min(kGridG - 1, max(0, (int)((x - gbox[0]) * gbox[3])));
+                const int cy = min(kGridG - 1, max(0, (int)((y - gbox[1]) * gbox[4])));
+                const int cz = min(kGridG - 1, max(0, (int)((z - gbox[2]) * gbox[5])));
+                return (cz * kGridG + cy) * kGridG + cx;
+            };
+            for (int k = tid; k < n; k += kEmdThreads) atomicAdd(cell_fill + cell_of(ox[k], oy[k], oz[k]), 1);
+            __syncthreads();
+            if (warp == 0) {   // exclusive scan of the 512 counts: 16 per lane
+                int loc[kGridCells / 32], sum = 0;
+#pragma unroll
+                for (int i = 0; i < kGridCells / 32; ++i) { loc[i] = cell_fill[lane * (kGridCells / 32) + i]; sum += loc[i]; }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int run = incl - sum;
+#pragma unroll
+                for (int i = 0; i < kGridCells / 32; ++i) {
+                    cell_start[lane * (kGridCells / 32) + i] = run;
+                    cell_fill[lane * (kGridCells / 32) + i] = run;
+                    run += loc[i];
+                }
+                if (lane == 31) cell_start[kGridCells] = run;
+            }
+            __syncthreads();
+            for (int k = tid; k < n; k += kEmdThreads) {
+                const int pos = atomicAdd(cell_fill + cell_of(ox[k], oy[k], oz[k]), 1);
+                gx[pos] = ox[k]; gy[pos] = oy[k]; gz[pos] = oz[k]; gperm[pos] = k;
+            }
+        }
+    }
     cluster.sync();
 
     int solo_from = -1;
@@ -347,11 +451,134 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         if (total_u == 0) break;  // uniform across the cluster; later iterations cannot change anything
         const int mine = hi - lo;
 
+        // ---- 2./3. Bid with the object grid: one warp per bidder.  The warp visits the 3x3x3 block of cells around the
+        // bidder, then the next shell, ... every object it meets is evaluated exactly.  After a shell of Chebyshev radius
+        // rr, every unvisited object is at least rr cells away along some axis, i.e. farther than `covered`; once that is
+        // at least the pruning radius R = 3 - better + 2e-6 (an object can change the top two only if sqrt(s) < R, prices
+        // being >= 0) nothing unvisited can matter and the scan stops -- the same exact cut-off as the full scan below.
+        const bool grid_now = use_grid && total_u >= p.grid_min_u;
+        if (grid_now) {
+            int *next_bidder = reinterpret_cast<int *>(gred + 7);
+            if (tid == 0) *next_bidder = 0;
+            __syncthreads();
+            for (;;) {   // bidders need different numbers of shells: warps take them from a counter
+                int a0 = 0;
+                if (lane == 0) a0 = atomicAdd(next_bidder, 1);
+                a0 = __shfl_sync(0xffffffffu, a0, 0);
+                if (a0 >= mine) break;
+                int a = lo + a0, hr = 0;
+                if (S > 1) {
+                    while (hr < S - 1 && a >= ucount[hr]) { a -= ucount[hr]; ++hr; }
+                }
+                const int jl = *(cluster.map_shared_rank(list, hr) + a);
+                const int j = hr * ns + jl;
+                const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
+                const int bcx = min(kGridG - 1, max(0, (int)((x1 - gbox[0]) * gbox[3])));
+                const int bcy = min(kGridG - 1, max(0, (int)((y1 - gbox[1]) * gbox[4])));
+                const int bcz = min(kGridG - 1, max(0, (int)((z1 - gbox[2]) * gbox[5])));
+                Top2 r, m;
+                int run_incl = 0, run_beg = 0, run_n = 0;   // this lane's run: inclusive prefix of lengths, first object
+                // The objects of x-adjacent cells are contiguous in the sorted arrays: the (2rr+1)^3 block around the bidder
+                // is (2rr+1)^2 runs.  Their objects are spread evenly over the lanes, four independent evaluations in
+                // flight per lane.  rr = 1, then 2 (the whole block again, from scratch); beyond that every object.
+                float Rprev2 = 3.0e38f;   // squared pruning radius known from the previous shell (exact cut-off)
+                for (int rr = 1;; ++rr) {
+                    r.best = kNegInit; r.better = kNegInit; r.idx = -1;
+                    int total;
+                    if (rr <= 2) {
+                        const int side = 2 * rr + 1, nruns = side * side;
+                        int len = 0, beg = 0;
+                        if (lane < nruns) {
+                            const int dz = lane / side - rr, dy = lane - (lane / side) * side - rr;
+                            const int cy = bcy + dy, cz = bcz + dz;
+                            if ((unsigned)cy < (unsigned)kGridG && (unsigned)cz < (unsigned)kGridG) {
+                                const int rowc = (cz * kGridG + cy) * kGridG;
+                                beg = cell_start[rowc + max(0, bcx - rr)];
+                                len = cell_start[rowc + min(kGridG - 1, bcx + rr) + 1] - beg;
+                            }
+                        }
+                        int incl = len;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        run_incl = incl; run_beg = beg; run_n = nruns;
+                        total = __shfl_sync(0xffffffffu, incl, 31);
+                    } else {
+                        total = n;                     // everything (rare: the radius exceeds two cells)
+                    }
+                    for (int base0 = 0; base0 < total; base0 += 128) {   // warp-uniform trip count (shuffles inside)
+                        const int pos0 = base0 + lane;
+                        int ks[4], os[4];
+                        float ss[4], vs[4];
+                        if (rr <= 2) {
+                            // run of each of the lane's four positions: the number of runs whose inclusive prefix is <= pos
+                            int q[4] = {0, 0, 0, 0};
+                            for (int t2 = 0; t2 < run_n; ++t2) {
+                                const int pre = __shfl_sync(0xffffffffu, run_incl, t2);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) q[i] += (pre <= pos0 + 32 * i);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int qq = min(q[i], 31);
+                                const int b0 = __shfl_sync(0xffffffffu, run_beg, qq);
+                                const int pinc = __shfl_sync(0xffffffffu, run_incl, max(qq - 1, 0));
+                                os[i] = b0 + (pos0 + 32 * i - (qq ? pinc : 0));
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) os[i] = pos0 + 32 * i;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            ks[i] = -1; ss[i] = 0.f;
+                            if (pos0 + 32 * i < total) {
+                                const int o = os[i];
+                                ss[i] = sqdist_exact(gx[o] - x1, gy[o] - y1, gz[o] - z1);
+                                if (ss[i] <= Rprev2) ks[i] = gperm[o];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            vs[i] = (float)(3.0 - (double)__fsqrt_rn(ss[i]) - (double)price[ks[i] < 0 ? 0 : ks[i]]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int k = ks[i];
+                            const float v = vs[i];
+                            if (k >= 0) {   // objects arrive in no particular order: equal values keep the lowest index
+                                if (v > r.best) { r.better = r.best; r.best = v; r.idx = k; }
+                                else if (v == r.best) { r.better = r.best; r.idx = min(r.idx, k); }
+                                else if (v > r.better) r.better = v;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    m = r;
+                    warp_top2_redux(m);
+                    if (rr > 2) break;
+                    const float R = (3.0f - m.better) + 2e-6f;
+                    const float covered = (float)rr * gbox[6] - gbox[7];
+                    if (covered >= R * 1.000001f) break;
+                    Rprev2 = R * R * 1.000001f;   // as in the full scan: sqrt(s) > R cannot change the top two
+                }
+                if (lane == 0) {
+                    const float inc = __fadd_rn(__fsub_rn(m.best, m.better), p.eps);
+                    *(cluster.map_shared_rank(bid, hr) + jl) = m.idx;
+                    *(cluster.map_shared_rank(bid_inc, hr) + jl) = inc;
+                    if (m.idx >= 0) {
+                        const int orank = m.idx / ns;
+                        atomic_max_float(cluster.map_shared_rank(max_inc, orank) + (m.idx - orank * ns), inc);
+                    }
+                }
+            }
+        }
         // ---- 2./3. Bid (emd_cuda.cu:95-179): G bidders at a time, tpb threads per bidder
         // The bidders are processed in passes of G = a power of two bidders (tpb = 1024 / G threads each).  One pass of
         // the next power of two >= mine wastes up to half of the lanes: take that pass only if at least 3/4 of its groups
         // are real, else a full pass of half the size and continue with the remainder.
-        for (int a0 = 0, G = 1; a0 < mine; a0 += G) {
+        for (int a0 = 0, G = 1; a0 < mine && !grid_now; a0 += G) {
             const int rem = mine - a0;
             G = 1;
             while (G < rem && G < kEmdThreads) G <<= 1;
@@ -620,12 +847,15 @@ static size_t emd_smem_bytes(int n, int S) {
     const int ns = n / S;
     return sizeof(float) * (size_t)(4 * n) + sizeof(float) * (size_t)(7 * ns) + sizeof(float) * (32 * 3 + 8 + 4);
 }
+static size_t emd_grid_bytes(int n) { return sizeof(float) * ((size_t)4 * n + (kGridCells + 4) + kGridCells + 8 + 8 + 32 * 64); }
 static size_t emd_solo_bytes(int n) { return sizeof(float) * ((size_t)9 * n + 2 * kSoloMax + 2 + 2 * kSoloMax); }
 
 }  // namespace psd
 
 using namespace psd;
 
+static int g_emd_grid = 1;
+int psd_set_emd_grid(int enable) { const int old = g_emd_grid; if (enable == 0 || enable == 1) g_emd_grid = enable; return old; }
 static int g_emd_solo = 1;
 int psd_set_emd_solo(int enable) { const int old = g_emd_solo; if (enable == 0 || enable == 1) g_emd_solo = enable; return old; }
 
@@ -649,6 +879,8 @@ cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, 
     while (S < 8 && emd_smem_bytes(n, S) > (size_t)max_smem) S *= 2;
     if (emd_smem_bytes(n, S) > (size_t)max_smem || (n % S) != 0) { *unsupported = 1; return cudaSuccess; }
     size_t smem = emd_smem_bytes(n, S);
+    const int grid = (smem + emd_grid_bytes(n) <= (size_t)max_smem && g_emd_grid) ? 1 : 0;
+    if (grid) smem += emd_grid_bytes(n);
     const int solo = (smem + emd_solo_bytes(n) <= (size_t)max_smem && g_emd_solo) ? 1 : 0;
     if (solo) smem += emd_solo_bytes(n);
     cudaError_t e = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -656,7 +888,11 @@ cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, 
     EmdParams p;
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.dist = dist; p.assignment = assignment; p.price = price;
     p.assignment_inv = assignment_inv; p.max_increments = max_increments; p.bid = bid; p.bid_increments = bid_increments;
-    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = solo;
+    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = solo; p.grid = grid;
+    {
+        const char *ev = getenv("PSD_EMD_GRID_MIN_U");
+        p.grid_min_u = ev ? atoi(ev) : 36 * S;   // measured optimum at config 3 (S = 4): 144 = a little more than one bidder per warp
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned int)(b * S));
     cfg.blockDim = dim3(kEmdThreads);

@@ -22,6 +22,7 @@ cudaError_t psd_launch_nn_f64(const void *src, const void *dst, int in_f64, int 
                               int *indices, cudaStream_t stream);
 int psd_icp_max_points();
 int psd_set_emd_solo(int enable);
+int psd_set_emd_grid(int enable);
 cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
                                  cudaStream_t stream);
 cudaError_t psd_launch_fps(const float *xyz, int b, int n, int npoint, int start, long long *centroids, cudaStream_t stream);
@@ -188,6 +189,8 @@ int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_sr
 int psd_chamfer_nn_variant(int variant) { return psd_set_nn_variant(variant); }
 
 int psd_emd_solo_mode(int enable) { return psd_set_emd_solo(enable); }
+
+int psd_emd_grid_mode(int enable) { return psd_set_emd_grid(enable); }
 
 int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
 

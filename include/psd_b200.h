@@ -215,6 +215,9 @@ int psd_chamfer_nn_variant(int variant);
  * cluster finishes the auction alone, one warp per bidder, without cluster barriers; results are identical).  enable: 0 / 1
  * sets it, anything else only queries; returns the previous setting.  Default 1. */
 int psd_emd_solo_mode(int enable);
+/* The same kind of switch for the auction kernel's object grid (bidders visit the grid cells around them shell by shell and
+ * stop at their exact pruning radius instead of testing all n objects; results are identical).  Default 1. */
+int psd_emd_grid_mode(int enable);
 
 /* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
  * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a

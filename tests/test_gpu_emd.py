@@ -27,14 +27,26 @@ def run_cluster(pkg, dev, x, y, eps, iters, cluster):
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("cfg", [("uniform", 3, 1024, 0.005, 50), ("clustered", 2, 2048, 0.005, 50), ("uniform", 2, 1024, 0.05, 300),
-                                 ("lattice", 2, 1024, 0.005, 20), ("uniform", 1, 2048, 0.002, 7), ("uniform", 2, 1024, 0.005, 1)])
+                                 ("lattice", 2, 1024, 0.005, 20), ("uniform", 1, 2048, 0.002, 7), ("uniform", 2, 1024, 0.005, 1),
+                                 ("dup", 2, 1024, 0.005, 30), ("offset", 2, 1024, 0.005, 30), ("uniform", 1, 4096, 0.005, 12)])
 def test_emd_bit_exact_all_cluster_sizes(pkg, oracle, cuda, cluster, cfg):
     kind, b, n, eps, iters = cfg
     x, y = make_clouds(kind, b, n, n, seed=100 + n + iters)
-    dist, ass, price, inv = run_cluster(pkg, cuda, x, y, eps, iters, cluster)
     wd, wa, state = oracle.emd_forward(x, y, eps, iters, nthreads=8, full_state=True)
-    assert (ass == wa).all(), f"assignment differs in {(ass != wa).sum()} places"
-    assert (dist.view(np.uint32) == wd.view(np.uint32)).all()
+    import os
+    # with the object grid (default threshold: only iterations with many bidders), with the grid in EVERY iteration
+    # (PSD_EMD_GRID_MIN_U=0: exercises the second shell and the every-object fallback), and without it
+    for grid, min_u in ((1, None), (1, "0"), (0, None)):
+        oldg = pkg._lib.lib.psd_emd_grid_mode(grid)
+        if min_u is not None:
+            os.environ["PSD_EMD_GRID_MIN_U"] = min_u
+        try:
+            dist, ass, price, inv = run_cluster(pkg, cuda, x, y, eps, iters, cluster)
+        finally:
+            pkg._lib.lib.psd_emd_grid_mode(oldg)
+            os.environ.pop("PSD_EMD_GRID_MIN_U", None)
+        assert (ass == wa).all(), f"grid={grid} min_u={min_u}: assignment differs in {(ass != wa).sum()} places"
+        assert (dist.view(np.uint32) == wd.view(np.uint32)).all()
     if iters > 1 and kind != "lattice":  # the last iteration's price/assignment_inv writes race in the reference too
         pass
 
@@ -51,14 +63,16 @@ def test_emd_solo_mode_training_setting(pkg, oracle, cuda, cluster, cfg):
     wd, wa, state = oracle.emd_forward(x, y, eps, iters, nthreads=8, full_state=True)
     lib = pkg._lib.lib
     res = {}
-    for solo in (1, 0):
-        old = lib.psd_emd_solo_mode(solo)
+    for solo, grid in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        old, oldg = lib.psd_emd_solo_mode(solo), lib.psd_emd_grid_mode(grid)
         try:
-            res[solo] = run_cluster(pkg, cuda, x, y, eps, iters, cluster)
+            out = run_cluster(pkg, cuda, x, y, eps, iters, cluster)
         finally:
-            lib.psd_emd_solo_mode(old)
-        dist, ass, price, inv = res[solo]
-        assert (ass == wa).all(), f"solo={solo}: assignment differs in {(ass != wa).sum()} places"
+            lib.psd_emd_solo_mode(old); lib.psd_emd_grid_mode(oldg)
+        if grid:
+            res[solo] = out
+        dist, ass, price, inv = out
+        assert (ass == wa).all(), f"solo={solo} grid={grid}: assignment differs in {(ass != wa).sum()} places"
         assert (dist.view(np.uint32) == wd.view(np.uint32)).all()
     if iters == 3000:   # converged long before the last iteration: no forced assignment, the scratch state is deterministic
         for k in (2, 3):

@@ -891,7 +891,7 @@ cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, 
     p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = solo; p.grid = grid;
     {
         const char *ev = getenv("PSD_EMD_GRID_MIN_U");
-        p.grid_min_u = ev ? atoi(ev) : 36 * S;   // measured optimum at config 3 (S = 4): 144 = a little more than one bidder per warp
+        p.grid_min_u = ev ? atoi(ev) : 144;   // measured optimum for cluster sizes 2, 4 and 8 (sweep 0 ... 1024 at B = 64, 32, 8)
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned int)(b * S));

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 // The objects of x-adjacent cells are contiguous in the sorted arrays: the (2rr+1)^3 block around the bidder
                 // is (2rr+1)^2 runs.  Their objects are spread evenly over the lanes, four independent evaluations in
                 // flight per lane.  rr = 1, then 2 (the whole block again, from scratch); beyond that every object.
-                float Rprev2 = 3.0e38f;   // squared pruning radius known from the previous shell (exact cut-off)
+                float Rprev2 = 3.0e38f, Rgprev = 3.0e38f;   // pruning radius known from the previous shell: R^2 and 3 - better
                 for (int rr = 1;; ++rr) {
                     r.best = kNegInit; r.better = kNegInit; r.idx = -1;
                     int total;
@@ -537,7 +537,14 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                             if (pos0 + 32 * i < total) {
                                 const int o = os[i];
                                 ss[i] = sqdist_exact(gx[o] - x1, gy[o] - y1, gz[o] - z1);
-                                if (ss[i] <= Rprev2) ks[i] = gperm[o];
+                                if (ss[i] <= Rprev2) {
+                                    // inside the radius known from the previous shell; as in the full scan, the object's own
+                                    // price tightens it: v > better needs sqrt(s) < 3 - better - price[k]
+                                    const int k = gperm[o];
+                                    const float pk = price[k];
+                                    const float Rk = (Rgprev - pk) + (4e-6f + 1e-6f * (fabsf(Rgprev) + fabsf(pk)));
+                                    if (Rk > 0.f && ss[i] <= Rk * Rk * 1.000002f) ks[i] = k;
+                                }
                             }
                         }
 #pragma unroll
@@ -562,6 +569,10 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                     const float covered = (float)rr * gbox[6] - gbox[7];
                     if (covered >= R * 1.000001f) break;
                     Rprev2 = R * R * 1.000001f;   // as in the full scan: sqrt(s) > R cannot change the top two
+                    Rgprev = 3.0f - m.better;
+                    // a radius beyond two cells cannot be covered by the 5x5x5 block either (it only shrinks if far, cheap
+                    // objects beat the near ones): go straight to the every-object pass
+                    if (rr == 1 && 2.0f * gbox[6] - gbox[7] < R * 1.000001f) rr = 2;
                 }
                 if (lane == 0) {
                     const float inc = __fadd_rn(__fsub_rn(m.best, m.better), p.eps);

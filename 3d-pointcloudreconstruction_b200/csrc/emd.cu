@@ -220,6 +220,83 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         }
         return r;
     }
+    if (tpb >= 32 && ((n / tpb) & 3) == 0) {
+        // A warp (or several) per bidder, many objects per lane: two passes without any per-step dependency on earlier
+        // evaluations.  Pass 1: fp32 bounds of every value (as above) and the warp's second best lower bound g2.  Pass 2: the
+        // same sweep again, exact evaluation only of the objects whose upper bound reaches g2 (a handful per warp).  The
+        // adaptive-radius scan below is a chain of ~2 k cycles per step for such a warp: the radius of the bidders that are
+        // still unassigned late in the auction is large, so most steps took its slow path.
+        const unsigned int sx = (unsigned int)__cvta_generic_to_shared(ox), sy = (unsigned int)__cvta_generic_to_shared(oy),
+                           sz = (unsigned int)__cvta_generic_to_shared(oz);
+        float a1 = kNegInit, a2 = kNegInit;
+        auto bounds4 = [&](int k, float (&sv)[4], float (&au)[4], float (&al)[4]) {
+            float4 xa, ya, za;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
+            const float4 pk = *reinterpret_cast<const float4 *>(price + k);
+            const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, zs[4] = {za.x, za.y, za.z, za.w};
+            const float ps[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sv[i] = sqdist_exact(xs[i] - x1, ys[i] - y1, zs[i] - z1);
+                float d;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(sv[i]));   // relative error <= 2^-23
+                const float a = (3.0f - d) - ps[i];
+                const float delta = 1e-6f * (3.0f + d + fabsf(ps[i]));   // |a - v| <= 3.6e-7 (3 + d + |p|)
+                al[i] = a - delta;
+                au[i] = a + delta;
+            }
+        };
+        // pass 1 on every fourth chunk only: ANY two objects give a valid lower bound of the final second best; a quarter of
+        // them gives one that still leaves only a handful of candidates
+        for (int k = 4 * t; k < n; k += 16 * tpb) {
+            float sv[4], au[4], al[4];
+            bounds4(k, sv, au, al);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a2 = fmaxf(a2, fminf(a1, al[i]));
+                a1 = fmaxf(a1, al[i]);
+            }
+        }
+        const unsigned int o1 = ford(a1);
+        const unsigned int m1 = __reduce_max_sync(0xffffffffu, o1);
+        const bool holder = o1 == m1;
+        const int nh = __popc(__ballot_sync(0xffffffffu, holder));
+        const float g2 = nh >= 2 ? funord(m1) : funord(__reduce_max_sync(0xffffffffu, ford(holder ? a2 : a1)));
+        // pass 2 in the squared domain (no sqrt): v >= g2 needs sqrt(s) <= (3 - g2) - price + delta; delta2 bounds the delta
+        // of pass 1 for every object that can pass (d <= |c| + |p| + 1)
+        const float c = 3.0f - g2;
+        for (int k = 4 * t; k < n; k += 4 * tpb) {
+            float4 xa, ya, za;
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
+            const float4 pk = *reinterpret_cast<const float4 *>(price + k);
+            const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, zs[4] = {za.x, za.y, za.z, za.w};
+            const float ps[4] = {pk.x, pk.y, pk.z, pk.w};
+            float sv[4];
+            bool cs[4];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sv[i] = sqdist_exact(xs[i] - x1, ys[i] - y1, zs[i] - z1);
+                const float rhs = (c - ps[i]) + 2e-6f * (4.0f + fabsf(c) + 2.0f * fabsf(ps[i]));
+                cs[i] = valid && rhs > 0.f && sv[i] <= rhs * rhs * 1.000001f;
+                any |= cs[i];
+            }
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (__any_sync(0xffffffffu, cs[i])) {
+                        const float v = (float)(3.0 - (double)__fsqrt_rn(sv[i]) - (double)ps[i]);
+                        if (cs[i]) apply(k + i, v);
+                    }
+                }
+            }
+        }
+        return r;
+    }
     if (((n / tpb) & 3) == 0) {
         // four CONSECUTIVE objects per lane and step (3 x LDS.128), one vote for the common all-skipped case; a lane still
         // meets its objects in index order, and the group merge breaks ties by the lowest index.  The coordinates never

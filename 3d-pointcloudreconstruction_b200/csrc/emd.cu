@@ -378,8 +378,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     int *cell_fill = cell_start + kGridCells + 4;               // [kGridCells]
     float *gbox = reinterpret_cast<float *>(cell_fill + kGridCells);   // [8] min xyz, inverse cell size xyz, hmin, abs slack
     unsigned int *gred = reinterpret_cast<unsigned int *>(gbox + 8);    // [8] min / max reduction (ordered uints), ok flag
-    int *gruns = reinterpret_cast<int *>(gred + 8);                      // [32 warps][2][32] run begin / prefix of run lengths
-    float *after_grid = p.grid ? reinterpret_cast<float *>(gruns + 32 * 64) : reinterpret_cast<float *>(cnt + 4);
+    float *after_grid = p.grid ? reinterpret_cast<float *>(gred + 8) : reinterpret_cast<float *>(cnt + 4);
     // solo mode (only rank 0's copies are used): the whole cloud's sliced state gathered into full-length arrays
     float *F_maxinc = after_grid;                               // [n]
     int *F_winner = reinterpret_cast<int *>(F_maxinc + n);      // [n]
@@ -935,7 +934,7 @@ static size_t emd_smem_bytes(int n, int S) {
     const int ns = n / S;
     return sizeof(float) * (size_t)(4 * n) + sizeof(float) * (size_t)(7 * ns) + sizeof(float) * (32 * 3 + 8 + 4);
 }
-static size_t emd_grid_bytes(int n) { return sizeof(float) * ((size_t)4 * n + (kGridCells + 4) + kGridCells + 8 + 8 + 32 * 64); }
+static size_t emd_grid_bytes(int n) { return sizeof(float) * ((size_t)4 * n + (kGridCells + 4) + kGridCells + 8 + 8); }
 static size_t emd_solo_bytes(int n) { return sizeof(float) * ((size_t)9 * n + 2 * kSoloMax + 2 + 2 * kSoloMax); }
 
 }  // namespace psd

@@ -683,7 +683,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
             const int wl = tpb < 32 ? tpb : 32;
             Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
-            warp_merge_top2(r, wl);
+            if (wl == 32) warp_top2_redux(r);   // whole warp, one bidder: three redux.sync instead of five shuffle rounds
+            else warp_merge_top2(r, wl);
             if (tpb > 32) {  // bidder groups span several warps: finish through shared memory
                 __syncthreads();
                 if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }

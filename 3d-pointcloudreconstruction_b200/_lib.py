@@ -42,6 +42,7 @@ lib.psd_chamfer_loss_step_host_ex.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp,
 lib.psd_host_step_graphs.argtypes = [_ci]
 lib.psd_emd_solo_mode.argtypes = [_ci]
 lib.psd_emd_grid_mode.argtypes = [_ci]
+lib.psd_chamfer_tc_ctas.argtypes = [_ci]
 lib.psd_proj_min_dist.argtypes = [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp]
 lib.psd_icp_batch.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _ci, ctypes.c_double, _vp, _vp, _vp, _vp]
 lib.psd_nn_f64.argtypes = [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp]
@@ -52,14 +53,14 @@ lib.psd_debug_tc_filter.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp,
 for _n in ("psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward", "psd_emd_forward",
            "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward", "psd_chamfer_forward_host",
            "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant", "psd_debug_tc_filter", "psd_debug_tc_prof", "psd_chamfer_mean_loss_forward",
-           "psd_chamfer_mean_loss_backward", "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj"):
+           "psd_chamfer_mean_loss_backward", "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_chamfer_tc_ctas", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj"):
     getattr(lib, _n).restype = _ci
 
 EXPORTS = ("psd_version", "psd_last_error", "psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward",
            "psd_emd_forward", "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward",
            "psd_chamfer_forward_host", "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant",
            "psd_debug_tc_filter", "psd_debug_tc_prof", "psd_chamfer_mean_loss_forward", "psd_chamfer_mean_loss_backward",
-           "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj")
+           "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_chamfer_tc_ctas", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj")
 
 
 def last_error() -> str:

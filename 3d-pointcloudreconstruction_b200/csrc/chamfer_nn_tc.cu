@@ -852,6 +852,12 @@ bool psd_nn_tc_supported(const NNParams &p) {
     return (long long)p.blocks_dir0 * t0 + (long long)(p.total_blocks - p.blocks_dir0) * t1 < 0x3fffffffLL;
 }
 
+// Throughput-oriented callers that keep several launches in flight (a pipelined training loop) can give every launch a part
+// of the GPU: a CTA then owns twice as many units and its serial prologue and tail amortise, while a launch on another stream
+// fills the other SMs.  0 = one CTA per SM.
+static int g_tc_max_ctas = 0;
+int psd_set_tc_max_ctas(int n) { const int old = g_tc_max_ctas; if (n >= 0) g_tc_max_ctas = n; return old; }
+
 cudaError_t psd_launch_nn_tc(const NNParams &p_in, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -884,7 +890,8 @@ cudaError_t psd_launch_nn_tc(const NNParams &p_in, int num_sms, cudaStream_t str
     const int blocks1 = (p.total_blocks - p.blocks_dir0) * p.dir[1].ntt;
     p.blocks_dir0 = blocks0;
     p.total_blocks = blocks0 + blocks1;
-    const int grid = p.total_blocks < num_sms ? p.total_blocks : num_sms;
+    int grid = p.total_blocks < num_sms ? p.total_blocks : num_sms;
+    if (g_tc_max_ctas > 0 && grid > g_tc_max_ctas) grid = g_tc_max_ctas;
     if (dbg || prof) tc::chamfer_nn_tc_kernel<true><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, dbg, dbg_ld, prof);
     else tc::chamfer_nn_tc_kernel<false><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, nullptr, 0, nullptr);
     cudaError_t e = cudaGetLastError();

@@ -23,6 +23,7 @@ cudaError_t psd_launch_nn_f64(const void *src, const void *dst, int in_f64, int 
 int psd_icp_max_points();
 int psd_set_emd_solo(int enable);
 int psd_set_emd_grid(int enable);
+int psd_set_tc_max_ctas(int n);
 cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
                                  cudaStream_t stream);
 cudaError_t psd_launch_fps(const float *xyz, int b, int n, int npoint, int start, long long *centroids, cudaStream_t stream);
@@ -192,6 +193,8 @@ int psd_emd_solo_mode(int enable) { return psd_set_emd_solo(enable); }
 
 int psd_emd_grid_mode(int enable) { return psd_set_emd_grid(enable); }
 
+int psd_chamfer_tc_ctas(int max_ctas) { return psd_set_tc_max_ctas(max_ctas); }
+
 int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
 
 int psd_debug_tc_filter(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist1, float *dist2, int *idx1,
@@ -291,13 +294,13 @@ static cudaError_t enqueue_loss_step(const float *xyz1_host, const float *xyz2_h
 // cudaGraphLaunch replaces the nine API calls of a step (the host side, not the GPU, bounds a 40 µs step otherwise).
 struct StepGraph {
     const void *x1 = nullptr, *x2 = nullptr, *loss = nullptr, *g1 = nullptr, *g2 = nullptr, *ws = nullptr;
-    int b = 0, n = 0, m = 0, variant = 0, device = -1;
+    int b = 0, n = 0, m = 0, variant = 0, device = -1, tc_ctas = 0;
     cudaGraphExec_t exec = nullptr;
     bool plain = false;   // capture was not possible (pageable buffers, stream already capturing): keep the plain path
     unsigned long long last_use = 0;
     bool same(const StepGraph &o) const {
         return x1 == o.x1 && x2 == o.x2 && loss == o.loss && g1 == o.g1 && g2 == o.g2 && ws == o.ws && b == o.b && n == o.n &&
-               m == o.m && variant == o.variant && device == o.device;
+               m == o.m && variant == o.variant && device == o.device && tc_ctas == o.tc_ctas;
     }
 };
 static const int kStepGraphs = 64;
@@ -353,7 +356,7 @@ int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host
     if (g_step_graph_enabled && stream != nullptr && stream != cudaStreamLegacy) {
         StepGraph key;
         key.x1 = xyz1_host; key.x2 = xyz2_host; key.loss = loss_host; key.g1 = gradxyz1_host; key.g2 = gradxyz2_host;
-        key.ws = ws; key.b = b; key.n = n; key.m = m; key.variant = psd_set_nn_variant(-1);
+        key.ws = ws; key.b = b; key.n = n; key.m = m; key.variant = psd_set_nn_variant(-1); key.tc_ctas = psd_set_tc_max_ctas(-1);
         cudaGetDevice(&key.device);
         StepGraph *hit = nullptr, *victim = &g_step_graph[0];
         for (StepGraph &g : g_step_graph) {

@@ -243,25 +243,41 @@ def main():
         g2 = gbuf[p][3 * B * N:].view(B, M, 3)
         assert pkg.chamfer_3D.backward(xs[p], ys[p], g1, g2, gd1[p], gd2[p], i1[p], i2[p]) == 1, L.last_error()
 
+    CHAINS = 4
+    TC_CTAS = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // CHAINS)
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         for s in range(W):  # untimed warm-up (also loads the module before graph capture)
             step(s)
         stream.synchronize()
-        # steps are independent batches: even steps are captured on the launch stream, odd ones on a forked side stream, so
-        # that the small backward kernels of a step may run beside the forward of the next one (as they do in the
-        # pipelined host loop); every step still runs its full forward + zero + backward
-        side = torch.cuda.Stream(device=dev)
+        # one launch at a time on all SMs: the serial picture of a step (reported as config.serial_ms_per_step)
+        L.lib.psd_chamfer_tc_ctas(0)
+        gser = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gser, stream=stream):
+            for s in range(50):
+                step(W + s)
+        gser.replay(); stream.synchronize()
+        serial_ms = min(event_time_ms(torch, gser.replay, stream) for _ in range(3)) / 50
+        # Steps are independent batches, so CHAINS of them are kept in flight (as in the pipelined host loop): step s is
+        # captured on chain s % CHAINS, and every launch of the tensor-core NN kernel is limited to num_sms / CHAINS CTAs
+        # (psd_chamfer_tc_ctas).  A CTA then owns CHAINS times as many units, so its serial prologue and tail amortise, while
+        # the launches of the other chains fill the remaining SMs (tools/tc_split_probe.py: 37.0 us per forward with one launch
+        # at a time, 28.7 us with four 37-CTA launches in flight).  Every step still runs its full forward + zero + backward.
+        L.lib.psd_chamfer_tc_ctas(TC_CTAS)
+        sides = [torch.cuda.Stream(device=dev) for _ in range(CHAINS - 1)]
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            side.wait_stream(stream)
+            for sd in sides:
+                sd.wait_stream(stream)
             for s in range(K):
-                if s & 1:
-                    with torch.cuda.stream(side):
+                c = s % CHAINS
+                if c:
+                    with torch.cuda.stream(sides[c - 1]):
                         step(W + s)
                 else:
                     step(W + s)
-            stream.wait_stream(side)
+            for sd in sides:
+                stream.wait_stream(sd)
         graph.replay()  # one untimed replay
         stream.synchronize()
 
@@ -326,6 +342,7 @@ def main():
         loss.backward()
         return loss.item()
 
+    L.lib.psd_chamfer_tc_ctas(0)   # one step at a time in the torch-API and blocking legs: all SMs per launch
     loss_mod = pkg.Loss()
     for s in range(W):
         e2e_step_torch(s)
@@ -339,7 +356,6 @@ def main():
     Ke = min(K, 400)
     for s in range(W):
         e2e_step(s)
-    e2e_run_pipelined(W + 2 * DEPTH)   # every (buffer, slot) combination seen twice: its CUDA graph is cached
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -348,6 +364,10 @@ def main():
         e2e_step(s)
     torch.cuda.synchronize()
     e2e_sync_ms = (time.perf_counter() - t0) * 1e3
+    L.lib.psd_chamfer_tc_ctas(TC_CTAS)   # DEPTH steps in flight: the launches share the SMs (captured into the step graphs)
+    e2e_run_pipelined(W + 2 * DEPTH)   # every (buffer, slot) combination seen twice: its CUDA graph is cached
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_run_pipelined(Ke)
@@ -383,10 +403,11 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"chamfer3D fwd+bwd B={B} per GPU, N=M={N}, fp32, bit-exact idx (BASELINE configs[1])",
                    "cache": f"inputs larger than L2: {pool} batches x {per_batch / 1e6:.1f} MB rotate, one per step",
-                   "timing": "K steps captured in one CUDA graph (even / odd steps as two independent chains, so a step's backward may overlap the next step's forward), CUDA events on the launch stream, max over ranks",
+                   "timing": f"K steps captured in one CUDA graph as {CHAINS} independent chains (step s on chain s % {CHAINS}), every tensor-core NN launch limited to {TC_CTAS} CTAs so that {CHAINS} launches share the SMs; CUDA events on the launch stream, max over ranks",
+                   "serial_ms_per_step": serial_ms, "serial_note": "the same step with one launch at a time on all SMs",
                    "parallelism": f"batch-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 4 * 3 * B * (N + M), "d2h_bytes_per_step": 4,
-                "steps": Ke, "pipeline_depth": DEPTH,
+                "steps": Ke, "pipeline_depth": DEPTH, "tc_ctas_per_launch": TC_CTAS,
                 "api": "psd_chamfer_loss_step_host_ex (C ABI, pinned host buffers), pipelined: per step H2D + chamfer fwd + mean loss [loss/loss.py:36] + bwd + D2H loss; up to 8 steps in flight on 8 streams/workspaces, each replayed from a cached CUDA graph, so the H2D copies (1.57 MB = 32 us at ~49 GB/s PCIe, the bound) and the host latency overlap the kernels; every step's loss is read on the host",
                 "synchronous": {"value": e2e_sync_value, "unit": "pairs/s", "api": "psd_chamfer_loss_step_host: the same step, one blocking call per step (no overlap)"},
                 "torch_api": {"value": e2e_torch_value, "unit": "pairs/s", "api": "Loss().get_chamfer_loss(pred, gt); loss.backward(); loss.item() with a pinned-host H2D copy per step"}},
@@ -396,8 +417,9 @@ def main():
     if emd_all is not None:
         out["emd_all_gpus"] = emd_all
 
+    L.lib.psd_chamfer_tc_ctas(0)
     if rank == 0:
-        # ---- roofline of the dominant kernel: chamfer_nn_kernel alone, back-to-back launches, CUDA events
+        # ---- roofline of the dominant kernel: chamfer_nn_kernel alone (one launch at a time, all SMs), back-to-back launches, CUDA events
         reps = 50
         with torch.cuda.stream(stream):
             for s in range(5):

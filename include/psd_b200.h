@@ -218,6 +218,11 @@ int psd_emd_solo_mode(int enable);
 /* The same kind of switch for the auction kernel's object grid (bidders visit the grid cells around them shell by shell and
  * stop at their exact pruning radius instead of testing all n objects; results are identical).  Default 1. */
 int psd_emd_grid_mode(int enable);
+/* Upper bound on the CTAs of one launch of the tensor-core NN kernel (0 = one per SM, the default; a negative value only
+ * queries).  A caller that keeps several launches in flight on different streams (a pipelined training loop) can set it to
+ * half the SM count: every CTA then owns twice as many units, so its serial prologue and tail amortise, and the launch on
+ * the other stream fills the remaining SMs.  Returns the previous value.  Results are identical. */
+int psd_chamfer_tc_ctas(int max_ctas);
 
 /* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
  * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a

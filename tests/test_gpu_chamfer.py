@@ -222,6 +222,29 @@ def test_host_buffer_loss_pipeline_graph_replay(pkg, oracle, cuda, depth):
         assert abs(g0 - g1) <= 1e-6 * abs(g0)
 
 
+@pytest.mark.parametrize("ctas", [1, 37, 74, 0])
+def test_tensor_core_kernel_with_capped_grid(pkg, oracle, cuda, ctas):
+    """psd_chamfer_tc_ctas: a launch limited to a part of the SMs (for callers that keep several launches in flight) gives the
+    same bits; two capped launches on two streams at once as well."""
+    lib = pkg._lib.lib
+    x, y = make_clouds("uniform", 24, 1024, 1100, seed=77)
+    want = oracle.chamfer_forward(x, y, nthreads=8)
+    tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    oldv, oldc = lib.psd_chamfer_nn_variant(3), lib.psd_chamfer_tc_ctas(ctas)
+    try:
+        outs = []
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        for s in streams:
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                outs.append(pkg.chamfer_3DDist()(tx, ty))
+        torch.cuda.synchronize()
+    finally:
+        lib.psd_chamfer_nn_variant(oldv); lib.psd_chamfer_tc_ctas(oldc)
+    for out in outs:
+        assert_bit_equal([t.cpu().numpy() for t in out], want, f"ctas={ctas}")
+
+
 def test_backward_raw_accumulates_into_given_buffers(pkg, oracle, cuda):
     """chamfer_3D.backward adds onto the caller's buffers (the reference relies on caller-zeroed grads)."""
     x, y = make_clouds("uniform", 2, 256, 300, seed=21)

@@ -243,8 +243,8 @@ def main():
         g2 = gbuf[p][3 * B * N:].view(B, M, 3)
         assert pkg.chamfer_3D.backward(xs[p], ys[p], g1, g2, gd1[p], gd2[p], i1[p], i2[p]) == 1, L.last_error()
 
-    CHAINS = 4
-    TC_CTAS = max(1, torch.cuda.get_device_properties(dev).multi_processor_count // CHAINS)
+    CHAINS = int(os.environ.get("PSD_BENCH_CHAINS", "8"))
+    TC_CTAS = int(os.environ.get("PSD_BENCH_TC_CTAS", "0")) or max(1, torch.cuda.get_device_properties(dev).multi_processor_count // 4)
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         for s in range(W):  # untimed warm-up (also loads the module before graph capture)
@@ -258,11 +258,13 @@ def main():
                 step(W + s)
         gser.replay(); stream.synchronize()
         serial_ms = min(event_time_ms(torch, gser.replay, stream) for _ in range(3)) / 50
-        # Steps are independent batches, so CHAINS of them are kept in flight (as in the pipelined host loop): step s is
-        # captured on chain s % CHAINS, and every launch of the tensor-core NN kernel is limited to num_sms / CHAINS CTAs
-        # (psd_chamfer_tc_ctas).  A CTA then owns CHAINS times as many units, so its serial prologue and tail amortise, while
-        # the launches of the other chains fill the remaining SMs (tools/tc_split_probe.py: 37.0 us per forward with one launch
-        # at a time, 28.7 us with four 37-CTA launches in flight).  Every step still runs its full forward + zero + backward.
+        # Steps are independent batches, so CHAINS (8) of them are kept in flight (as in the pipelined host loop): step s is
+        # captured on chain s % CHAINS, and every launch of the tensor-core NN kernel is limited to a quarter of the SMs
+        # (psd_chamfer_tc_ctas(37)).  A CTA then owns four times as many units, so its serial prologue and tail amortise, and
+        # with twice as many launches in flight as SM quarters a finished CTA's SM is taken over at once by a waiting launch
+        # (tools/tc_split_probe.py: 37.0 us per forward with one launch at a time, 26.8 us with eight 37-CTA launches in
+        # flight; sweep of chains x cap in profiles/r1_chamfer_nn_tc_summary.md).  Every step still runs its full forward +
+        # zero + backward.
         L.lib.psd_chamfer_tc_ctas(TC_CTAS)
         sides = [torch.cuda.Stream(device=dev) for _ in range(CHAINS - 1)]
         graph = torch.cuda.CUDAGraph()
@@ -403,7 +405,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"chamfer3D fwd+bwd B={B} per GPU, N=M={N}, fp32, bit-exact idx (BASELINE configs[1])",
                    "cache": f"inputs larger than L2: {pool} batches x {per_batch / 1e6:.1f} MB rotate, one per step",
-                   "timing": f"K steps captured in one CUDA graph as {CHAINS} independent chains (step s on chain s % {CHAINS}), every tensor-core NN launch limited to {TC_CTAS} CTAs so that {CHAINS} launches share the SMs; CUDA events on the launch stream, max over ranks",
+                   "timing": f"K steps captured in one CUDA graph as {CHAINS} independent chains (step s on chain s % {CHAINS}), every tensor-core NN launch limited to {TC_CTAS} CTAs so that the launches in flight share the SMs; CUDA events on the launch stream, max over ranks",
                    "serial_ms_per_step": serial_ms, "serial_note": "the same step with one launch at a time on all SMs",
                    "parallelism": f"batch-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 4 * 3 * B * (N + M), "d2h_bytes_per_step": 4,

@@ -484,8 +484,16 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                     run += loc[i];
                 }
                 if (lane == 31) cell_start[kGridCells] = run;
+                int mx = 0;
+#pragma unroll
+                for (int i = 0; i < kGridCells / 32; ++i) mx = max(mx, loc[i]);
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                if (lane == 0) gred[7] = (unsigned int)mx;   // (slot 7 is the bidder counter of the iterations later on)
             }
             __syncthreads();
+            // a cloud that piles a quarter of its objects into one cell (tight clusters plus outliers) gains nothing from
+            // the grid: every block would hold most of the objects
+            if ((int)gred[7] * 4 > n) use_grid = false;
             for (int k = tid; k < n; k += kEmdThreads) {
                 const int pos = atomicAdd(cell_fill + cell_of(ox[k], oy[k], oz[k]), 1);
                 gx[pos] = ox[k]; gy[pos] = oy[k]; gz[pos] = oz[k]; gperm[pos] = k;

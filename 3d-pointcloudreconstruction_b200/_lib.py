@@ -22,45 +22,49 @@ _vp = ctypes.c_void_p
 _ci = ctypes.c_int
 _cf = ctypes.c_float
 
+# every export of include/psd_b200.h with its argument types (all return int unless noted)
+_SIGNATURES = {
+    "psd_chamfer_forward": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp],
+    "psd_chamfer_forward_ex": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _cf, _vp, _ci, _ci, _vp],
+    "psd_chamfer_backward": [_vp] * 8 + [_ci, _ci, _ci, _vp],
+    "psd_chamfer_backward_ex": [_vp] * 8 + [_ci, _ci, _ci, _ci, _ci, _vp],
+    "psd_emd_forward": [_vp, _vp, _ci, _ci, _ci] + [_vp] * 12 + [_cf, _ci, _vp],
+    "psd_emd_forward_fresh": [_vp, _vp, _ci, _ci, _vp, _vp, _cf, _ci, _vp],
+    "psd_emd_forward_cluster": [_vp, _vp, _ci, _ci, _vp, _vp, _vp, _vp, _cf, _ci, _ci, _vp],
+    "psd_emd_backward": [_vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp],
+    "psd_emd_backward_ex": [_vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _vp],
+    "psd_emd_mean_loss_forward": [_vp, _vp, _ci, _ci, _vp, _vp, _cf, _ci, _vp, _vp, _vp],
+    "psd_emd_mean_loss_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp],
+    "psd_chamfer_forward_host": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp],
+    "psd_fp32_fma_peak": [_cf, ctypes.POINTER(_cf), _vp],
+    "psd_chamfer_stats": [ctypes.POINTER(ctypes.c_longlong), _ci],
+    "psd_chamfer_nn_variant": [_ci],
+    "psd_chamfer_mean_loss_forward": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "psd_chamfer_mean_loss_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _vp],
+    "psd_chamfer_mean_loss_backward_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp],
+    "psd_chamfer_loss_step_host": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp],
+    "psd_chamfer_loss_step_host_ex": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp],
+    "psd_chamfer_loss_step_pred_dev": [_vp, _ci, _vp, _ci, _ci, _ci, _vp, _vp, _ci, _ci, _vp],
+    "psd_host_step_graphs": [_ci],
+    "psd_emd_solo_mode": [_ci],
+    "psd_emd_grid_mode": [_ci],
+    "psd_chamfer_tc_ctas": [_ci],
+    "psd_proj_min_dist": [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],
+    "psd_icp_batch": [_vp, _vp, _ci, _ci, _ci, _vp, _ci, ctypes.c_double, _vp, _vp, _vp, _vp],
+    "psd_nn_f64": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],
+    "psd_farthest_point_sample": [_vp, _ci, _ci, _ci, _ci, _vp, _vp],
+    "psd_cont_proj": [_vp, _ci, _ci, _ci, _ci, ctypes.c_float, _vp, _vp],
+    "psd_cont_proj_backward": [_vp, _vp, _ci, _ci, _ci, _ci, ctypes.c_float, _vp, _vp],
+    "psd_debug_tc_prof": [_vp],
+    "psd_debug_tc_filter": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _ci, _vp],
+}
 lib.psd_version.restype = _ci
 lib.psd_last_error.restype = ctypes.c_char_p
-lib.psd_chamfer_forward.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp]
-lib.psd_chamfer_forward_ex.argtypes = [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _cf, _vp, _ci, _ci, _vp]
-lib.psd_chamfer_backward.argtypes = [_vp] * 8 + [_ci, _ci, _ci, _vp]
-lib.psd_emd_forward.argtypes = [_vp, _vp, _ci, _ci, _ci] + [_vp] * 12 + [_cf, _ci, _vp]
-lib.psd_emd_forward_fresh.argtypes = [_vp, _vp, _ci, _ci, _vp, _vp, _cf, _ci, _vp]
-lib.psd_emd_forward_cluster.argtypes = [_vp, _vp, _ci, _ci, _vp, _vp, _vp, _vp, _cf, _ci, _ci, _vp]
-lib.psd_emd_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp]
-lib.psd_chamfer_forward_host.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp]
-lib.psd_fp32_fma_peak.argtypes = [_cf, ctypes.POINTER(_cf), _vp]
-lib.psd_chamfer_stats.argtypes = [ctypes.POINTER(ctypes.c_longlong), _ci]
-lib.psd_chamfer_nn_variant.argtypes = [_ci]
-lib.psd_chamfer_mean_loss_forward.argtypes = [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
-lib.psd_chamfer_mean_loss_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _vp]
-lib.psd_chamfer_loss_step_host.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp]
-lib.psd_chamfer_loss_step_host_ex.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _vp]
-lib.psd_host_step_graphs.argtypes = [_ci]
-lib.psd_emd_solo_mode.argtypes = [_ci]
-lib.psd_emd_grid_mode.argtypes = [_ci]
-lib.psd_chamfer_tc_ctas.argtypes = [_ci]
-lib.psd_proj_min_dist.argtypes = [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp]
-lib.psd_icp_batch.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _ci, ctypes.c_double, _vp, _vp, _vp, _vp]
-lib.psd_nn_f64.argtypes = [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp]
-lib.psd_farthest_point_sample.argtypes = [_vp, _ci, _ci, _ci, _ci, _vp, _vp]
-lib.psd_cont_proj.argtypes = [_vp, _ci, _ci, _ci, _ci, ctypes.c_float, _vp, _vp]
-lib.psd_debug_tc_prof.argtypes = [_vp]
-lib.psd_debug_tc_filter.argtypes = [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _ci, _vp]
-for _n in ("psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward", "psd_emd_forward",
-           "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward", "psd_chamfer_forward_host",
-           "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant", "psd_debug_tc_filter", "psd_debug_tc_prof", "psd_chamfer_mean_loss_forward",
-           "psd_chamfer_mean_loss_backward", "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_chamfer_tc_ctas", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj"):
+for _n, _a in _SIGNATURES.items():
+    getattr(lib, _n).argtypes = _a
     getattr(lib, _n).restype = _ci
 
-EXPORTS = ("psd_version", "psd_last_error", "psd_chamfer_forward", "psd_chamfer_forward_ex", "psd_chamfer_backward",
-           "psd_emd_forward", "psd_emd_forward_fresh", "psd_emd_forward_cluster", "psd_emd_backward",
-           "psd_chamfer_forward_host", "psd_fp32_fma_peak", "psd_chamfer_stats", "psd_chamfer_nn_variant",
-           "psd_debug_tc_filter", "psd_debug_tc_prof", "psd_chamfer_mean_loss_forward", "psd_chamfer_mean_loss_backward",
-           "psd_chamfer_loss_step_host", "psd_chamfer_loss_step_host_ex", "psd_host_step_graphs", "psd_emd_solo_mode", "psd_emd_grid_mode", "psd_chamfer_tc_ctas", "psd_proj_min_dist", "psd_icp_batch", "psd_nn_f64", "psd_farthest_point_sample", "psd_cont_proj")
+EXPORTS = ("psd_version", "psd_last_error") + tuple(_SIGNATURES)
 
 
 def last_error() -> str:

@@ -40,6 +40,8 @@ def backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2) -
     _lib.check_tensor("idx2", idx2, torch.int32)
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
+    if xyz1.shape[2] != 3 or xyz2.shape[2] != 3 or xyz2.shape[0] != b:
+        raise RuntimeError("chamfer_3D.backward: expected xyz1 [B,N,3] and xyz2 [B,M,3]")
     if gradxyz1.numel() != b * n * 3 or gradxyz2.numel() != b * m * 3:
         raise RuntimeError("chamfer_3D.backward: gradient tensors have the wrong size")
     with torch.cuda.device(xyz1.device):
@@ -50,13 +52,15 @@ def backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2) -
 
 def forward_ex(xyz1, xyz2, dist1, dist2, idx1, idx2, layout=0, sums=None, fs_thr=1e-4, fs_count=None, q_begin=0,
                q_count=-1) -> int:
-    """psd_chamfer_forward_ex: fused loss sums / F-score counts, [B,3,N] layout, query slicing."""
-    if layout == 0:
-        b, n, _ = xyz1.shape
-        m = xyz2.shape[1]
-    else:
-        b, _, n = xyz1.shape
-        m = xyz2.shape[2]
+    """psd_chamfer_forward_ex: fused loss sums / F-score counts, query slicing, and the layout bit mask
+    (1: xyz1 is a contiguous [B,3,N] tensor, 2: xyz2 is a contiguous [B,3,M] tensor; else [B,N,3])."""
+    if layout not in (0, 1, 2, 3):
+        raise ValueError("layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]")
+    b = xyz1.shape[0]
+    n = xyz1.shape[2] if layout & 1 else xyz1.shape[1]
+    m = xyz2.shape[2] if layout & 2 else xyz2.shape[1]
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[1 if layout & 1 else 2] != 3 or xyz2.shape[1 if layout & 2 else 2] != 3:
+        raise RuntimeError("chamfer_3D.forward_ex: clouds must be [B,N,3] (or [B,3,N] where the layout mask says so)")
     for name, t, dt in (("xyz1", xyz1, torch.float32), ("xyz2", xyz2, torch.float32), ("dist1", dist1, torch.float32),
                         ("dist2", dist2, torch.float32), ("idx1", idx1, torch.int32), ("idx2", idx2, torch.int32)):
         _lib.check_tensor(name, t, dt)

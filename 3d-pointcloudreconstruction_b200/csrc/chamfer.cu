@@ -20,7 +20,10 @@
 //     order with strict '<'.  Otherwise (near-ties, duplicated points, non-finite input) the query takes
 //     an exact full scan that also reproduces the reference's NaN/512-tile semantics.
 //   => dist/idx are always produced by the exact formula; the filter only decides where to look.
+#include <cooperative_groups.h>
+
 #include "chamfer_nn.cuh"
+#include "psd_device.h"
 
 namespace psd {
 
@@ -447,11 +450,19 @@ __global__ void __launch_bounds__(kThreads, 1) chamfer_nn_kernel(const NNParams 
 
 // ------------------------------------------------------------------------------------------------
 // Backward: replaces both NmDistanceGradKernel launches (chamfer3D.cu:155-195) with one kernel.
-// One thread per (direction, cloud, point).  g = 2*graddist; v = g*(a - b[idx]) with the subtraction
+// One term per (direction, cloud, point): g = 2*graddist; v = g*(a - b[idx]) with the subtraction
 // rounded before the multiply, exactly as the reference's SASS (FADD, FMUL, no FMA);
-// own-point term: grad_a[j] += v (unique address per direction -> plain red.add),
-// scatter term  : grad_b[idx] -= v, aggregated inside the warp first: lanes that hit the same target
-// (__match_any_sync on idx) are summed by the lowest lane of the group and issue one atomic per axis.
+//   own-point term: grad_a[j]   += v   (one term per address and direction)
+//   scatter term  : grad_b[idx] -= v   aggregated inside the warp first: lanes that hit the same target
+//                   (__match_any_sync) are summed by the lowest lane of the group, one atomic per axis.
+// Two forms:
+//   OVERWRITE = false  the reference's contract (chamfer3D.cu:177-178): accumulate into caller-zeroed buffers, every
+//                      term an atomic.
+//   OVERWRITE = true   the gradients need no initialisation: phase 1 STORES the own-point terms (every element of
+//                      both gradients is written exactly once), a grid-wide barrier (cooperative launch), then phase 2
+//                      adds the scatter terms.  No memset before the launch and half the atomics.
+// Clouds and their gradients are addressed through (point, component) strides, so the generator's native
+// [B,3,N] layout (train.py:160-163) needs no transpose copy in either direction.
 // ------------------------------------------------------------------------------------------------
 struct GradParams {
     const float *xyz1, *xyz2;
@@ -461,65 +472,105 @@ struct GradParams {
     int b, n, m;
     long long total1;  // b*n
     long long total;   // b*(n+m)
+    long long ps1, cs1, ps2, cs2;   // point / component stride (floats) of cloud 1 and 2; the gradients use the same
     // mean-loss mode (gd1 == gd2 == nullptr): graddist1[e] = *upstream / cnt1, graddist2[e] = *upstream / cnt2 -- what
     // autograd hands to the reference's backward for loss = mean(dist1) + mean(dist2) (loss/loss.py:36)
     const float *upstream;
     float cnt1, cnt2;
 };
 
-__global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = gid < p.total;
-    const bool d2 = gid >= p.total1;
-    const long long e = active ? (d2 ? gid - p.total1 : gid) : 0;  // flat (cloud, point) index in its direction
-    const int na = d2 ? p.m : p.n, nb = d2 ? p.n : p.m;
-    const float *a = d2 ? p.xyz2 : p.xyz1;
-    const float *bq = d2 ? p.xyz1 : p.xyz2;
-    float *ga = d2 ? p.g2 : p.g1;
-    float *gb = d2 ? p.g1 : p.g2;
-    const float *gd = d2 ? p.gd2 : p.gd1;
-    const int *idx = d2 ? p.idx2 : p.idx1;
+struct GradTerm {
+    bool d2;            // direction 2 (cloud 2's points are the queries)
+    long long own;      // float offset of component 0 of the own point in its cloud / gradient
+    long long tgt;      // float offset of component 0 of the matched point in the other cloud / gradient
+    float v[3];
+};
 
-    float vx = 0.f, vy = 0.f, vz = 0.f;
-    long long tgt = -1 - (long long)(threadIdx.x & 31);  // inactive lanes: unique negative ids, never matched
-    if (active) {
-        const long long cloud = e / na;
-        const int j2 = idx[e];
-        const float gdv = gd ? gd[e] : __fdiv_rn(p.upstream ? *p.upstream : 1.0f, d2 ? p.cnt2 : p.cnt1);
-        const float g = gdv * 2.0f;
-        const float *pa = a + e * 3;
-        tgt = cloud * nb + j2;
-        const float *pb = bq + tgt * 3;
-        vx = __fmul_rn(g, __fsub_rn(pa[0], pb[0]));
-        vy = __fmul_rn(g, __fsub_rn(pa[1], pb[1]));
-        vz = __fmul_rn(g, __fsub_rn(pa[2], pb[2]));
-        float *o = ga + e * 3;
-        atomicAdd(o + 0, vx);
-        atomicAdd(o + 1, vy);
-        atomicAdd(o + 2, vz);
+__device__ __forceinline__ GradTerm grad_term(const GradParams &p, long long gid) {
+    GradTerm t;
+    t.d2 = gid >= p.total1;
+    const long long e = t.d2 ? gid - p.total1 : gid;  // flat (cloud, point) index in its direction
+    const int na = t.d2 ? p.m : p.n, nb = t.d2 ? p.n : p.m;
+    const float *a = t.d2 ? p.xyz2 : p.xyz1;
+    const float *bq = t.d2 ? p.xyz1 : p.xyz2;
+    const long long psa = t.d2 ? p.ps2 : p.ps1, csa = t.d2 ? p.cs2 : p.cs1;
+    const long long psb = t.d2 ? p.ps1 : p.ps2, csb = t.d2 ? p.cs1 : p.cs2;
+    const float *gd = t.d2 ? p.gd2 : p.gd1;
+    const int *idx = t.d2 ? p.idx2 : p.idx1;
+    const long long cloud = p.total < 0x7fffffffLL ? (long long)((int)e / na) : e / na;
+    const int j = (int)(e - cloud * na);
+    const int j2 = __ldg(idx + e);
+    const float gdv = gd ? __ldg(gd + e) : __fdiv_rn(p.upstream ? __ldg(p.upstream) : 1.0f, t.d2 ? p.cnt2 : p.cnt1);
+    const float g = gdv * 2.0f;
+    t.own = cloud * 3 * na + j * psa;
+    t.tgt = cloud * 3 * nb + j2 * psb;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t.v[k] = __fmul_rn(g, __fsub_rn(__ldg(a + t.own + k * csa), __ldg(bq + t.tgt + k * csb)));
+    return t;
+}
+
+// warp-aggregated scatter of one term per lane (inactive lanes carry unique negative targets and zero values)
+template <bool OVERWRITE>
+__device__ __forceinline__ void grad_scatter(const GradParams &p, bool active, const GradTerm &t, int lane) {
+    if (!OVERWRITE && active) {
+        float *o = (t.d2 ? p.g2 : p.g1) + t.own;
+        const long long csa = t.d2 ? p.cs2 : p.cs1;
+        atomicAdd(o, t.v[0]);
+        atomicAdd(o + csa, t.v[1]);
+        atomicAdd(o + 2 * csa, t.v[2]);
     }
-    // warp-aggregated scatter (the direction is warp-uniform only if total1 % 32 == 0, so the direction
-    // bit is folded into the match key).
-    const unsigned long long mkey = ((unsigned long long)tgt << 1) | (unsigned long long)(d2 ? 1 : 0);
+    // (the direction is warp-uniform only if total1 % 32 == 0, so the direction bit is folded into the match key)
+    const unsigned long long mkey = ((unsigned long long)t.tgt << 1) | (unsigned long long)(t.d2 ? 1 : 0);
     const unsigned int peers = __match_any_sync(0xffffffffu, mkey);
-    const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
-    float sx = vx, sy = vy, sz = vz;
+    float sx = t.v[0], sy = t.v[1], sz = t.v[2];
     // the lowest lane of every group adds its peers' terms in lane order; the loop trip count is the
     // largest group size minus one (zero for clouds without shared nearest neighbours in the warp).
     unsigned int rest = (lane == leader) ? (peers & ~(1u << lane)) : 0u;
     while (__any_sync(0xffffffffu, rest != 0u)) {
         const int src = rest ? __ffs(rest) - 1 : lane;
-        const float ox = __shfl_sync(0xffffffffu, vx, src);
-        const float oy = __shfl_sync(0xffffffffu, vy, src);
-        const float oz = __shfl_sync(0xffffffffu, vz, src);
+        const float ox = __shfl_sync(0xffffffffu, t.v[0], src);
+        const float oy = __shfl_sync(0xffffffffu, t.v[1], src);
+        const float oz = __shfl_sync(0xffffffffu, t.v[2], src);
         if (rest) { sx += ox; sy += oy; sz += oz; rest &= rest - 1u; }
     }
     if (active && lane == leader) {
-        float *o = gb + tgt * 3;
-        atomicAdd(o + 0, -sx);
-        atomicAdd(o + 1, -sy);
-        atomicAdd(o + 2, -sz);
+        float *o = (t.d2 ? p.g1 : p.g2) + t.tgt;
+        const long long csb = t.d2 ? p.cs1 : p.cs2;
+        atomicAdd(o, -sx);
+        atomicAdd(o + csb, -sy);
+        atomicAdd(o + 2 * csb, -sz);
+    }
+}
+
+template <bool OVERWRITE>
+__global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;   // a multiple of 32
+    const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // the thread's first term stays in registers across the barrier (most launches have one term per thread)
+    const bool active0 = gid0 < p.total;
+    GradTerm t0;
+    t0.d2 = false; t0.own = 0; t0.tgt = -1 - (long long)lane; t0.v[0] = t0.v[1] = t0.v[2] = 0.f;
+    if (active0) t0 = grad_term(p, gid0);
+    if (OVERWRITE) {
+        auto store_own = [&](const GradTerm &t) {
+            float *o = (t.d2 ? p.g2 : p.g1) + t.own;
+            const long long csa = t.d2 ? p.cs2 : p.cs1;
+            o[0] = t.v[0]; o[csa] = t.v[1]; o[2 * csa] = t.v[2];
+        };
+        if (active0) store_own(t0);
+        for (long long gid = gid0 + nthreads; gid < p.total; gid += nthreads) store_own(grad_term(p, gid));
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+    }
+    grad_scatter<OVERWRITE>(p, active0, t0, lane);
+    for (long long base = gid0 - lane + nthreads; base < p.total; base += nthreads) {   // warp-uniform trip count
+        const bool active = base + lane < p.total;
+        GradTerm t;
+        t.d2 = false; t.own = 0; t.tgt = -1 - (long long)lane; t.v[0] = t.v[1] = t.v[2] = 0.f;
+        if (active) t = grad_term(p, base + lane);   // the second visit is served by L1 / L2
+        grad_scatter<OVERWRITE>(p, active, t, lane);
     }
 }
 
@@ -540,46 +591,42 @@ __global__ void chamfer_mean_loss_kernel(const float *__restrict__ sums, int b, 
 // ------------------------------------------------------------------------------------------------
 using namespace psd;
 
-static int g_num_sms = 0;
-static int g_max_smem = 0;
-static bool g_attr_set = false;
-static int g_nn_variant = 0;   // 0 = auto, 1 = shared-block kernel (this file), 2 = grouped kernel, 3 = tensor-core kernel
-static float *g_tc_dbg = nullptr;   // one-shot debug dump target of the tensor-core kernel (psd_debug_tc_filter)
-static int g_tc_dbg_ld = 0;
+// test / measurement switches (process-wide, atomics: safe to flip from any thread)
+static std::atomic<int> g_nn_variant{0};   // 0 = auto, 1 = FFMA kernel (this file), 3 = tensor-core kernel
+static std::atomic<float *> g_tc_dbg{nullptr};   // one-shot debug dump target of the tensor-core kernel (psd_debug_tc_filter)
+static std::atomic<int> g_tc_dbg_ld{0};
+static std::atomic<long long *> g_tc_prof{nullptr};
 
 bool psd_nn_tc_supported(const NNParams &p);                                               // chamfer_nn_tc.cu
-cudaError_t psd_launch_nn_tc(const NNParams &p, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b);
-static long long *g_tc_prof = nullptr;
-void psd_set_tc_prof(long long *prof) { g_tc_prof = prof; }
-cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int *error, int reset);
-void psd_set_tc_debug(float *dbg, int ld) { g_tc_dbg = dbg; g_tc_dbg_ld = ld; }
-
-cudaError_t psd_launch_nn_grouped(const NNParams &p, int num_sms, cudaStream_t stream);   // chamfer_nn_grouped.cu
-cudaError_t psd_read_chamfer_stats_grouped(unsigned long long *fallback, int reset);
+cudaError_t psd_launch_nn_tc(const NNParams &p, DeviceState *ds, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b);
+void psd_set_tc_prof(long long *prof) { g_tc_prof.store(prof); }
+cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int reset);
+void psd_set_tc_debug(float *dbg, int ld) { g_tc_dbg_ld.store(ld); g_tc_dbg.store(dbg); }
 
 int psd_set_nn_variant(int v) {
-    const int old = g_nn_variant;
-    if (v >= 0 && v <= 3) g_nn_variant = v;
-    return old;
+    if (v == 0 || v == 1 || v == 3) return g_nn_variant.exchange(v);
+    return g_nn_variant.load();
+}
+
+// layout: bit 0 = xyz1 is [B,3,N], bit 1 = xyz2 is [B,3,M] (else [B,N,3] / [B,M,3])
+static inline void layout_strides(int layout, int bit, int npts, long long &ps, long long &cs) {
+    if (layout & bit) { ps = 1; cs = npts; } else { ps = 3; cs = 1; }
 }
 
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
                                        float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
                                        int *fs_count, int q_begin, int q_count, cudaStream_t stream) {
     if (b <= 0 || n <= 0 || m <= 0) return cudaSuccess;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    cudaError_t derr = cudaSuccess;
+    DeviceState *ds = device_state(&derr);
+    if (ds == nullptr) return derr;
+    const int num_sms = ds->num_sms, max_smem = ds->max_smem;
     NNParams p;
     const int QB = kQB;
-    auto fill = [&](NNDirection &D, const float *q, int nq, const float *t, int nt, float *dist, int *idx, int slot) {
+    auto fill = [&](NNDirection &D, const float *q, int nq, int qbit, const float *t, int nt, int tbit, float *dist, int *idx, int slot) {
         D.q = q; D.t = t; D.nq = nq; D.nt = nt; D.dist = dist; D.idx = idx; D.slot = slot;
-        if (layout == 0) { D.q_ps = 3; D.q_cs = 1; D.t_ps = 3; D.t_cs = 1; }
-        else { D.q_ps = 1; D.q_cs = nq; D.t_ps = 1; D.t_cs = nt; }
+        layout_strides(layout, qbit, nq, D.q_ps, D.q_cs);
+        layout_strides(layout, tbit, nt, D.t_ps, D.t_cs);
         D.q_bs = 3LL * nq; D.t_bs = 3LL * nt;
         int qb0 = q_begin < 0 ? 0 : q_begin;
         if (qb0 > nq) qb0 = nq;
@@ -589,8 +636,8 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
         D.qblocks = (qc + QB - 1) / QB;
         D.ntt = 1; D.ws = nullptr;
     };
-    fill(p.dir[0], xyz1, n, xyz2, m, dist1, idx1, 0);
-    fill(p.dir[1], xyz2, m, xyz1, n, dist2, idx2, 1);
+    fill(p.dir[0], xyz1, n, 1, xyz2, m, 2, dist1, idx1, 0);
+    fill(p.dir[1], xyz2, m, 2, xyz1, n, 1, dist2, idx2, 1);
     const long long blocks = (long long)b * (p.dir[0].qblocks + p.dir[1].qblocks);
     if (blocks == 0) return cudaSuccess;
     if (blocks > 0x3fffffffLL) return cudaErrorInvalidConfiguration;
@@ -598,39 +645,36 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     p.total_blocks = (int)blocks;
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
     p.tile = 0; p.flush = 0;
-    // Tensor-core filter (chamfer_nn_tc.cu) whenever both target clouds fit its resident B operand.
+    // Tensor-core filter (chamfer_nn_tc.cu) for every launch of at least two units per SM.
     // Measured (tools/nn_variants.py): 41.5 vs 55.8 us at B=32 N=M=2048, 70.5 vs 105.8 us at B=64, 20.3 vs 22.5 us at
     // B=32 N=M=1024; launches of < 2 units per SM are latency-bound and stay on the FFMA kernel (8.9 vs 7.5 us at B=8 N=512).
-    if ((g_nn_variant == 3 || (g_nn_variant == 0 && blocks >= 2LL * g_num_sms)) && psd_nn_tc_supported(p)) {
-        float *dbg = g_tc_dbg;
-        g_tc_dbg = nullptr;
-        return psd_launch_nn_tc(p, g_num_sms, stream, dbg, g_tc_dbg_ld, g_tc_prof, b);
+    const int variant = g_nn_variant.load();
+    if ((variant == 3 || (variant == 0 && blocks >= 2LL * num_sms)) && psd_nn_tc_supported(p)) {
+        float *dbg = g_tc_dbg.exchange(nullptr);
+        return psd_launch_nn_tc(p, ds, stream, dbg, g_tc_dbg_ld.load(), g_tc_prof.load(), b);
     }
-    // Launches that give every 4-warp group of every SM at least two blocks run the grouped kernel (resolve and
-    // tile staging overlap the filter); smaller launches keep all 16 warps of a CTA on one block (latency).
-    // Measured (tools/nn_variants.py): +4 % at B=64 N=2048, but -25..-35 % for N >= 8192 -> auto only for small clouds.
-    const bool grouped = g_nn_variant == 2 ||
-                         (g_nn_variant == 0 && blocks >= 2LL * 4 * g_num_sms && n <= 4096 && m <= 4096);
-    if (grouped) return psd_launch_nn_grouped(p, g_num_sms, stream);
     // persistent grid: one CTA per SM, each takes a contiguous range of 128-query blocks
-    const int grid = blocks < g_num_sms ? (int)blocks : g_num_sms;
+    const int grid = blocks < num_sms ? (int)blocks : num_sms;
     const int per_cta = (int)((blocks + grid - 1) / grid);
     int tile = 1024;
     const int tmax = n > m ? n : m;
     while (tile < tmax && tile < 4096) tile *= 2;
     const size_t fixed = (size_t)tile * 16 + 2048;  // tile arrays + static shared memory + slack
     const size_t per_block = (size_t)kPerBlockBytes;
-    int flush = (int)(((size_t)g_max_smem - fixed) / per_block);
+    int flush = (int)(((size_t)max_smem - fixed) / per_block);
     if (flush > per_cta) flush = per_cta;
     if (flush < 1) flush = 1;
     p.tile = tile; p.flush = flush;
     const size_t smem = (size_t)tile * 16 + (size_t)flush * per_block + 64;
-    if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(chamfer_nn_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem - 1024);
-        if (e != cudaSuccess) return e;
-        g_attr_set = true;
+    {
+        std::lock_guard<std::mutex> lock(state_mutex());
+        if (!ds->attr_nn) {
+            cudaError_t e = cudaFuncSetAttribute(chamfer_nn_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(chamfer_nn_kernel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+            if (e != cudaSuccess) return e;
+            ds->attr_nn = true;
+        }
     }
     if (tile == 1024) chamfer_nn_kernel<1024><<<grid, kThreads, smem, stream>>>(p);
     else if (tile == 2048) chamfer_nn_kernel<2048><<<grid, kThreads, smem, stream>>>(p);
@@ -643,19 +687,49 @@ cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m,
     return cudaGetLastError();
 }
 
+// overwrite = 0: accumulate into caller-zeroed gradients (the reference's contract); 1: the gradients need no initialisation
 cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
-                                        int b, int n, int m, cudaStream_t stream, const float *upstream) {
+                                        int b, int n, int m, int layout, int overwrite, cudaStream_t stream, const float *upstream) {
     if (b <= 0 || (n <= 0 && m <= 0)) return cudaSuccess;
+    if (n <= 0 || m <= 0) {   // one cloud is empty: no pair exists, nothing to accumulate
+        if (!overwrite) return cudaSuccess;
+        cudaError_t e = n > 0 ? cudaMemsetAsync(gradxyz1, 0, sizeof(float) * 3 * (size_t)b * n, stream) : cudaSuccess;
+        if (e == cudaSuccess && m > 0) e = cudaMemsetAsync(gradxyz2, 0, sizeof(float) * 3 * (size_t)b * m, stream);
+        return e;
+    }
     GradParams p;
     p.upstream = upstream; p.cnt1 = (float)((long long)b * n); p.cnt2 = (float)((long long)b * m);
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.g1 = gradxyz1; p.g2 = gradxyz2; p.gd1 = graddist1; p.gd2 = graddist2;
     p.idx1 = idx1; p.idx2 = idx2; p.b = b; p.n = n; p.m = m;
     p.total1 = (long long)b * n;
     p.total = (long long)b * (n + m);
+    layout_strides(layout, 1, n, p.ps1, p.cs1);
+    layout_strides(layout, 2, m, p.ps2, p.cs2);
     const long long blocks = (p.total + 255) / 256;
-    chamfer_grad_kernel<<<(unsigned int)blocks, 256, 0, stream>>>(p);
-    return cudaGetLastError();
+    if (!overwrite) {
+        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        chamfer_grad_kernel<false><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    cudaError_t derr = cudaSuccess;
+    DeviceState *ds = device_state(&derr);
+    if (ds == nullptr) return derr;
+    int per_sm;
+    {
+        std::lock_guard<std::mutex> lock(state_mutex());
+        if (ds->grad_ctas_per_sm == 0) {
+            int occ = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chamfer_grad_kernel<true>, 256, 0);
+            if (e != cudaSuccess) return e;
+            ds->grad_ctas_per_sm = occ > 0 ? occ : 1;
+        }
+        per_sm = ds->grad_ctas_per_sm;
+    }
+    const long long resident = (long long)per_sm * ds->num_sms;   // a cooperative launch must be co-resident
+    const unsigned int grid = (unsigned int)(blocks < resident ? blocks : resident);
+    void *args[] = {(void *)&p};
+    return cudaLaunchCooperativeKernel((const void *)chamfer_grad_kernel<true>, dim3(grid), dim3(256), args, 0, stream);
 }
 
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {
@@ -667,13 +741,7 @@ cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {
         if (e != cudaSuccess) return e;
     }
     unsigned long long fg = 0;
-    e = psd_read_chamfer_stats_grouped(&fg, reset);
+    e = psd_read_chamfer_stats_tc(&fg, reset);
     *fallback += fg;
-    if (e != cudaSuccess) return e;
-    int tc_err = 0;
-    fg = 0;
-    e = psd_read_chamfer_stats_tc(&fg, &tc_err, reset);
-    *fallback += fg;
-    if (e == cudaSuccess && tc_err) e = cudaErrorLaunchTimeout;   // an mbarrier wait of the tensor-core kernel timed out
     return e;
 }

@@ -30,6 +30,7 @@
 // A unit is a block of 128 queries of one cloud/direction; a CTA owns a contiguous range of units.
 #include <cuda_fp16.h>
 #include "chamfer_nn.cuh"
+#include "psd_device.h"
 
 namespace psd {
 namespace tc {
@@ -65,7 +66,6 @@ constexpr int kSmemTC = kOffMisc + 64;
 static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8, "shared-memory carve-up alignment");
 
 __device__ unsigned long long g_fallback_queries_tc = 0ull;
-__device__ int g_tc_error = 0;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,8 +81,9 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must not hang the GPU.  On time-out the CTA-wide abort flag makes every later wait
-// fall through; the host sees g_tc_error and reports the launch as failed.
+// Bounded wait: a protocol bug must not hang the GPU.  After ~10 s (2e10 cycles: far beyond any legitimate wait, also
+// under compute-sanitizer) the kernel traps: the stream gets a sticky launch failure, so the next CUDA call of the
+// wrappers (and torch's next synchronise) raises instead of returning garbage dist / idx.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_flag) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
@@ -92,7 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
             if (*abort_flag) return;
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            if (now - t0 > 400000000LL) { *abort_flag = 1; atomicExch(&g_tc_error, 1); return; }
+            if (now - t0 > 20000000000LL) { *abort_flag = 1; __trap(); }
         }
     }
 }
@@ -815,6 +816,7 @@ __global__ void __launch_bounds__(256) chamfer_nn_tc_finalize_kernel(const NNPar
         cloud = (int)(e / D.q_count);
         const int j = D.q_begin + (int)(e - (long long)cloud * D.q_count);
         const unsigned long long key = D.ws[(long long)cloud * D.nq + j];
+        D.ws[(long long)cloud * D.nq + j] = ~0ull;   // the library-owned workspace is always left clean for the next launch
         const float *qp = D.q + (long long)cloud * D.q_bs + (long long)j * D.q_ps;
         const float d0 = exact_d(D.t + (long long)cloud * D.t_bs, D.t_ps, D.t_cs, 0, __ldg(qp), __ldg(qp + D.q_cs), __ldg(qp + 2 * D.q_cs));
         int ires;
@@ -855,67 +857,131 @@ bool psd_nn_tc_supported(const NNParams &p) {
 // Throughput-oriented callers that keep several launches in flight (a pipelined training loop) can give every launch a part
 // of the GPU: a CTA then owns twice as many units and its serial prologue and tail amortise, while a launch on another stream
 // fills the other SMs.  0 = one CTA per SM.
-static int g_tc_max_ctas = 0;
-int psd_set_tc_max_ctas(int n) { const int old = g_tc_max_ctas; if (n >= 0) g_tc_max_ctas = n; return old; }
+static std::atomic<int> g_tc_max_ctas{0};
+int psd_set_tc_max_ctas(int n) { return n >= 0 ? g_tc_max_ctas.exchange(n) : g_tc_max_ctas.load(); }
 
-cudaError_t psd_launch_nn_tc(const NNParams &p_in, int num_sms, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::chamfer_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTC);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::chamfer_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTC);
+// Merge workspace of the multi-tile mode: one grow-only buffer per (device, stream), owned by the library and ALWAYS left
+// filled with all-ones keys (the finalize kernel resets what it reads), so a launch costs neither an allocation nor a
+// memset.  Launches on one stream are ordered, launches on different streams get different buffers.  While `stream` is
+// being captured into a CUDA graph the launch takes a graph-owned allocation instead (cudaMallocAsync + memset +
+// cudaFreeAsync nodes, *temp = true): a graph must never hold a library pointer that a later launch may free.
+static cudaError_t acquire_merge_ws(DeviceState *ds, cudaStream_t stream, size_t elems, unsigned long long **out, bool *temp,
+                                    MergeWorkspace **slot_out) {
+    *temp = false; *slot_out = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(stream, &cap);
+    if (e != cudaSuccess) return e;
+    if (cap != cudaStreamCaptureStatusNone) {
+        // a graph must not hold a pointer that a later, larger launch may free: graph-owned memory for this launch
+        e = cudaMallocAsync(reinterpret_cast<void **>(out), elems * sizeof(unsigned long long), stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*out, 0xff, elems * sizeof(unsigned long long), stream);
+        *temp = true;
+        return e;
+    }
+    std::lock_guard<std::mutex> lock(state_mutex());
+    MergeWorkspace *hit = nullptr, *victim = &ds->merge[0];
+    for (MergeWorkspace &w : ds->merge) {
+        if (w.used && w.stream == stream) { hit = &w; break; }
+        if (!w.used) { if (victim->used) victim = &w; }
+        else if (victim->used && w.last_use < victim->last_use) victim = &w;
+    }
+    if (hit && hit->elems >= elems && !hit->dirty) {
+        hit->last_use = ++ds->merge_clock;
+        *out = hit->ptr; *slot_out = hit;
+        return cudaSuccess;
+    }
+    MergeWorkspace *w = hit ? hit : victim;
+    if (w->used && (w->elems < elems || w != hit)) {
+        // growing, or evicting another stream's buffer: whatever still uses it must have finished
+        e = (w == hit) ? cudaStreamSynchronize(stream) : cudaDeviceSynchronize();
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        cudaFree(w->ptr);
+        *w = MergeWorkspace();
+    }
+    if (w->ptr == nullptr) {
+        e = cudaMalloc(reinterpret_cast<void **>(&w->ptr), elems * sizeof(unsigned long long));
+        if (e != cudaSuccess) { *w = MergeWorkspace(); return e; }
+        w->elems = elems;
+        w->dirty = true;
+    }
+    if (w->dirty) {
+        e = cudaMemsetAsync(w->ptr, 0xff, w->elems * sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+        w->dirty = false;
+    }
+    w->used = true; w->stream = stream; w->last_use = ++ds->merge_clock;
+    *out = w->ptr; *slot_out = w;
+    return cudaSuccess;
+}
+
+cudaError_t psd_launch_nn_tc(const NNParams &p_in, DeviceState *ds, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b) {
+    {
+        std::lock_guard<std::mutex> lock(state_mutex());
+        if (!ds->attr_tc) {
+            cudaError_t e = cudaFuncSetAttribute(tc::chamfer_nn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTC);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::chamfer_nn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemTC);
+            if (e != cudaSuccess) return e;
+            ds->attr_tc = true;
+        }
     }
     NNParams p = p_in;
-    // target tiles; directions with more than one tile merge through a stream-ordered 64-bit workspace [B, nq]
+    // target tiles; directions with more than one tile (and at least one query) merge through the 64-bit workspace [B, nq]
     unsigned long long *ws = nullptr;
     size_t ws_elems = 0;
+    bool need_ws[2];
     for (int d = 0; d < 2; ++d) {
         p.dir[d].ntt = (p.dir[d].nt + tc::kMaxT - 1) / tc::kMaxT;
-        if (p.dir[d].ntt > 1) ws_elems += (size_t)b * p.dir[d].nq;
+        need_ws[d] = p.dir[d].ntt > 1 && p.dir[d].q_count > 0;
+        if (need_ws[d]) ws_elems += (size_t)b * p.dir[d].nq;
     }
+    bool ws_temp = false;
+    MergeWorkspace *ws_slot = nullptr;
     if (ws_elems) {
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&ws), ws_elems * sizeof(unsigned long long), stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ws, 0xff, ws_elems * sizeof(unsigned long long), stream);
+        cudaError_t e = acquire_merge_ws(ds, stream, ws_elems, &ws, &ws_temp, &ws_slot);
         if (e != cudaSuccess) return e;
     }
     {
         unsigned long long *w = ws;
         for (int d = 0; d < 2; ++d) {
-            p.dir[d].ws = p.dir[d].ntt > 1 ? w : nullptr;
-            if (p.dir[d].ntt > 1) w += (size_t)b * p.dir[d].nq;
+            p.dir[d].ws = need_ws[d] ? w : nullptr;
+            if (need_ws[d]) w += (size_t)b * p.dir[d].nq;
         }
     }
     const int blocks0 = p.blocks_dir0 * p.dir[0].ntt;
     const int blocks1 = (p.total_blocks - p.blocks_dir0) * p.dir[1].ntt;
     p.blocks_dir0 = blocks0;
     p.total_blocks = blocks0 + blocks1;
-    int grid = p.total_blocks < num_sms ? p.total_blocks : num_sms;
-    if (g_tc_max_ctas > 0 && grid > g_tc_max_ctas) grid = g_tc_max_ctas;
+    int grid = p.total_blocks < ds->num_sms ? p.total_blocks : ds->num_sms;
+    const int cap = g_tc_max_ctas.load();
+    if (cap > 0 && grid > cap) grid = cap;
     if (dbg || prof) tc::chamfer_nn_tc_kernel<true><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, dbg, dbg_ld, prof);
     else tc::chamfer_nn_tc_kernel<false><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, nullptr, 0, nullptr);
     cudaError_t e = cudaGetLastError();
     if (ws_elems) {
         if (e == cudaSuccess) {
             const long long total = (p.dir[0].ws ? (long long)b * p.dir[0].q_count : 0) + (p.dir[1].ws ? (long long)b * p.dir[1].q_count : 0);
-            tc::chamfer_nn_tc_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, b);
-            e = cudaGetLastError();
+            if (total > 0) {
+                tc::chamfer_nn_tc_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, b);
+                e = cudaGetLastError();
+            }
         }
-        const cudaError_t e2 = cudaFreeAsync(ws, stream);
-        if (e == cudaSuccess) e = e2;
+        if (ws_temp) {
+            const cudaError_t e2 = cudaFreeAsync(ws, stream);
+            if (e == cudaSuccess) e = e2;
+        } else if (e != cudaSuccess && ws_slot) {
+            std::lock_guard<std::mutex> lock(state_mutex());
+            ws_slot->dirty = true;   // a failed launch may have left keys behind: refill before the next use
+        }
     }
     return e;
 }
 
-cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int *error, int reset) {
+cudaError_t psd_read_chamfer_stats_tc(unsigned long long *fallback, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(fallback, tc::g_fallback_queries_tc, sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(error, tc::g_tc_error, sizeof(int));
     if (e != cudaSuccess) return e;
     if (reset) {
         const unsigned long long z = 0;
-        const int zi = 0;
         e = cudaMemcpyToSymbol(tc::g_fallback_queries_tc, &z, sizeof(z));
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol(tc::g_tc_error, &zi, sizeof(zi));
     }
     return e;
 }

@@ -25,6 +25,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "psd_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -53,7 +55,24 @@ struct EmdParams {
     int solo;   // 1: shared memory holds the solo-mode arrays (see emd_auction_kernel)
     int grid;   // 1: shared memory holds the object grid (cell-sorted copy of the objects)
     int grid_min_u;   // iterations with fewer bidders in the cluster use the full scan (a bidder per warp is latency bound)
+    float *gws;       // GLOBAL mode (n too large for shared memory): per-cloud state in global memory, 11 n floats per cloud
+    float *loss_sums; // optional [B]: loss_sums[cloud] += sum_j sqrt(dist[cloud, j])  (Loss.get_emd_loss, loss/loss.py:25)
 };
+
+// vector loads of four consecutive objects: shared memory (resident mode) or global memory through L2 (GLOBAL mode, where
+// the arrays are written by other CTAs of the cluster: ld.global.cg never looks at this SM's L1)
+template <bool GLOBAL>
+__device__ __forceinline__ float4 ld4(const float *base, unsigned int sbase, int k) {
+    float4 v;
+    if (GLOBAL) {
+        v = __ldcg(reinterpret_cast<const float4 *>(base + k));
+    } else {
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sbase + 4u * k));
+    }
+    return v;
+}
+template <bool GLOBAL>
+__device__ __forceinline__ float ld1(const float *ptr) { return GLOBAL ? __ldcg(ptr) : *ptr; }
 
 // float atomicMax with the reference's semantics (emd_cuda.cu:10-20): CAS loop, `val > old` in float.
 __device__ __forceinline__ void atomic_max_float(float *address, float val) {
@@ -123,6 +142,7 @@ __device__ __forceinline__ void warp_top2_redux(Top2 &r) {
 // '>' tie rule is unchanged) and the warp evaluates them together when some lane has two; `better` for the radius is then
 // the second best of the whole bidder group inside the warp (a valid lower bound of the final second best), not only the
 // lane's own.
+template <bool GLOBAL>
 __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, const float *oz, const float *price, int n,
                                             float x1, float y1, float z1, int tpb, int t, bool valid) {
     Top2 r;
@@ -140,8 +160,8 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
     };
     auto evaluate_queue = [&]() {
         // both values first (two independent sqrt / fp64 chains in flight), then the updates in index order
-        const float v0 = (float)(3.0 - (double)__fsqrt_rn(qs0) - (double)price[qk0]);
-        const float v1 = (float)(3.0 - (double)__fsqrt_rn(qs1) - (double)price[qk1]);
+        const float v0 = (float)(3.0 - (double)__fsqrt_rn(qs0) - (double)ld1<GLOBAL>(price + qk0));
+        const float v1 = (float)(3.0 - (double)__fsqrt_rn(qs1) - (double)ld1<GLOBAL>(price + qk1));
         if (qn > 0) apply(qk0, v0);
         if (qn > 1) apply(qk1, v1);
         qn = 0;
@@ -164,7 +184,7 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         if (pass) {
             // per-object test with the object's own price: v > better needs sqrt(s) < 3 - better - price[k].  The
             // slack covers the fp32 rounding of this test and of the reference's value (|terms| are O(1): 3 ulp(4)).
-            const float pk = price[k];
+            const float pk = ld1<GLOBAL>(price + k);
             const float Rk = (Rg - pk) + (4e-6f + 1e-6f * (fabsf(Rg) + fabsf(pk)));
             if (Rk > 0.f && s <= Rk * Rk * 1.000002f) {
                 if (qn == 0) { qk0 = k; qs0 = s; } else { qk1 = k; qs1 = s; }
@@ -189,8 +209,8 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
                 const int k = k0 + i * tpb;
                 au[i] = kNegInit; sv[i] = 0.f;
                 if (k < n && valid) {
-                    sv[i] = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
-                    const float pk = price[k];
+                    sv[i] = sqdist_exact(ld1<GLOBAL>(ox + k) - x1, ld1<GLOBAL>(oy + k) - y1, ld1<GLOBAL>(oz + k) - z1);
+                    const float pk = ld1<GLOBAL>(price + k);
                     float d;
                     asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(sv[i]));   // relative error <= 2^-23
                     const float a = (3.0f - d) - pk;
@@ -213,7 +233,7 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
                 const int k = k0 + i * tpb;
                 const bool cand = k < n && valid && au[i] >= g2;
                 if (__any_sync(0xffffffffu, cand)) {
-                    const float v = (float)(3.0 - (double)__fsqrt_rn(sv[i]) - (double)price[cand ? k : 0]);
+                    const float v = (float)(3.0 - (double)__fsqrt_rn(sv[i]) - (double)ld1<GLOBAL>(price + (cand ? k : 0)));
                     if (cand) apply(k, v);
                 }
             }
@@ -226,15 +246,12 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         // same sweep again, exact evaluation only of the objects whose upper bound reaches g2 (a handful per warp).  The
         // adaptive-radius scan below is a chain of ~2 k cycles per step for such a warp: the radius of the bidders that are
         // still unassigned late in the auction is large, so most steps took its slow path.
-        const unsigned int sx = (unsigned int)__cvta_generic_to_shared(ox), sy = (unsigned int)__cvta_generic_to_shared(oy),
-                           sz = (unsigned int)__cvta_generic_to_shared(oz);
+        const unsigned int sx = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(ox), sy = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(oy),
+                           sz = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(oz);
         float a1 = kNegInit, a2 = kNegInit;
         auto bounds4 = [&](int k, float (&sv)[4], float (&au)[4], float (&al)[4]) {
-            float4 xa, ya, za;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
-            const float4 pk = *reinterpret_cast<const float4 *>(price + k);
+            const float4 xa = ld4<GLOBAL>(ox, sx, k), ya = ld4<GLOBAL>(oy, sy, k), za = ld4<GLOBAL>(oz, sz, k);
+            const float4 pk = GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(price + k)) : *reinterpret_cast<const float4 *>(price + k);
             const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, zs[4] = {za.x, za.y, za.z, za.w};
             const float ps[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
@@ -268,11 +285,8 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         // of pass 1 for every object that can pass (d <= |c| + |p| + 1)
         const float c = 3.0f - g2;
         for (int k = 4 * t; k < n; k += 4 * tpb) {
-            float4 xa, ya, za;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
-            const float4 pk = *reinterpret_cast<const float4 *>(price + k);
+            const float4 xa = ld4<GLOBAL>(ox, sx, k), ya = ld4<GLOBAL>(oy, sy, k), za = ld4<GLOBAL>(oz, sz, k);
+            const float4 pk = GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(price + k)) : *reinterpret_cast<const float4 *>(price + k);
             const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w}, zs[4] = {za.x, za.y, za.z, za.w};
             const float ps[4] = {pk.x, pk.y, pk.z, pk.w};
             float sv[4];
@@ -302,13 +316,10 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         // meets its objects in index order, and the group merge breaks ties by the lowest index.  The coordinates never
         // change after the prologue, so they are read through explicit shared-space addresses (no generic -> shared window
         // arithmetic in the loop).
-        const unsigned int sx = (unsigned int)__cvta_generic_to_shared(ox), sy = (unsigned int)__cvta_generic_to_shared(oy),
-                           sz = (unsigned int)__cvta_generic_to_shared(oz);
+        const unsigned int sx = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(ox), sy = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(oy),
+                           sz = GLOBAL ? 0u : (unsigned int)__cvta_generic_to_shared(oz);
         for (int k = 4 * t; k < n; k += 4 * tpb) {
-            float4 xa, ya, za;
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(xa.x), "=f"(xa.y), "=f"(xa.z), "=f"(xa.w) : "r"(sx + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ya.x), "=f"(ya.y), "=f"(ya.z), "=f"(ya.w) : "r"(sy + 4u * k));
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(za.x), "=f"(za.y), "=f"(za.z), "=f"(za.w) : "r"(sz + 4u * k));
+            const float4 xa = ld4<GLOBAL>(ox, sx, k), ya = ld4<GLOBAL>(oy, sy, k), za = ld4<GLOBAL>(oz, sz, k);
             const float s0 = sqdist_exact(xa.x - x1, ya.x - y1, za.x - z1);
             const float s1 = sqdist_exact(xa.y - x1, ya.y - y1, za.y - z1);
             const float s2 = sqdist_exact(xa.z - x1, ya.z - y1, za.z - z1);
@@ -323,7 +334,7 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         }
     } else {
         for (int k = t; k < n; k += tpb) {
-            const float s = sqdist_exact(ox[k] - x1, oy[k] - y1, oz[k] - z1);
+            const float s = sqdist_exact(ld1<GLOBAL>(ox + k) - x1, ld1<GLOBAL>(oy + k) - y1, ld1<GLOBAL>(oz + k) - z1);
             consider(k, s, valid && s <= R2);
         }
     }
@@ -341,6 +352,13 @@ __device__ __forceinline__ void warp_merge_top2(Top2 &r, int wl) {
     }
 }
 
+// GLOBAL = false: the cloud's whole state lives in (distributed) shared memory (n <= 8192).
+// GLOBAL = true : clouds too large for that (the reference accepts any n % 1024 == 0, emd_cuda.cu:125-133,236-249): the same
+//                 auction with the object coordinates, prices and the sliced state in a per-cloud global workspace (L2
+//                 resident); a CTA's slice pointer is array + rank * ns, so a remote slice is plain pointer arithmetic.
+//                 The cluster barriers order the global accesses (release / acquire at cluster scope); mutable state that
+//                 other CTAs write is read through L2 (ld.global.cg / atomics).  No object grid, no solo phase.
+template <bool GLOBAL>
 __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -352,23 +370,28 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     const int base = rank * ns;     // first global index of the slice
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- shared memory carve-up (identical offsets in every CTA of the cluster)
-    float *ox = reinterpret_cast<float *>(smem_raw);
+    // ---- carve-up (identical offsets in every CTA of the cluster): shared memory, or the cloud's global workspace
+    float *gbase = GLOBAL ? p.gws + (size_t)cloud * 11 * n : reinterpret_cast<float *>(smem_raw);
+    float *ox = gbase;
     float *oy = ox + n;
     float *oz = oy + n;
     float *price = oz + n;
-    float *max_inc = price + n;                                // [ns] owner slice
-    int *winner = reinterpret_cast<int *>(max_inc + ns);        // [ns] owner slice
-    int *ass_inv = winner + ns;                                 // [ns] owner slice
-    int *assign = ass_inv + ns;                                 // [ns] home slice
-    int *bid = assign + ns;                                     // [ns] home slice
-    float *bid_inc = reinterpret_cast<float *>(bid + ns);       // [ns] home slice
-    int *list = reinterpret_cast<int *>(bid_inc + ns);          // [ns] compacted local bidder ids
-    float *w_best = reinterpret_cast<float *>(list + ns);       // [32] cross-warp merge scratch
+    float *sl = price + n;                                      // sliced arrays: [ns] each in shared memory, [n] each (this CTA's part at + base) in GLOBAL mode
+    const int sstride = GLOBAL ? n : ns, soff = GLOBAL ? base : 0;
+    float *max_inc = sl + soff;                                 // [ns] owner slice
+    int *winner = reinterpret_cast<int *>(sl + sstride) + soff;         // [ns] owner slice
+    int *ass_inv = reinterpret_cast<int *>(sl + 2 * sstride) + soff;    // [ns] owner slice
+    int *assign = reinterpret_cast<int *>(sl + 3 * sstride) + soff;     // [ns] home slice
+    int *bid = reinterpret_cast<int *>(sl + 4 * sstride) + soff;        // [ns] home slice
+    float *bid_inc = sl + 5 * sstride + soff;                           // [ns] home slice
+    int *list = reinterpret_cast<int *>(sl + 6 * sstride) + soff;       // [ns] compacted local bidder ids
+    float *w_best = GLOBAL ? reinterpret_cast<float *>(smem_raw) : sl + 7 * ns;   // [32] cross-warp merge scratch
     float *w_better = w_best + 32;
     int *w_idx = reinterpret_cast<int *>(w_better + 32);
     int *ucount = w_idx + 32;                                   // [8] bidder count of every rank
     int *cnt = ucount + 8;                                      // [1]
+    // slice of cluster rank r2 of a sliced array (given this CTA's slice pointer)
+    auto rmt = [&](auto *ptr, int r2) { return GLOBAL ? ptr + (r2 - rank) * ns : cluster.map_shared_rank(ptr, r2); };
     // object grid: the objects sorted by cell of a kGridG^3 grid over their bounding box
     float *gx = reinterpret_cast<float *>(cnt + 4);             // [n] cell-sorted coordinates
     float *gy = gx + n;
@@ -397,7 +420,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     const size_t cb = (size_t)cloud * n;
 
     // ---- load state (the caller pre-initialises it as emd_module.py:43-54; honour what is there)
-    for (int k = tid; k < n; k += kEmdThreads) {
+    // resident mode: every CTA keeps its own replica of all n objects and prices; GLOBAL mode: one copy, filled slice by slice
+    for (int k = (GLOBAL ? base : 0) + tid; k < (GLOBAL ? base + ns : n); k += kEmdThreads) {
         ox[k] = x2g[k * 3 + 0];
         oy[k] = x2g[k * 3 + 1];
         oz[k] = x2g[k * 3 + 2];
@@ -413,7 +437,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     // ---- object grid (every CTA builds its own copy).  A bidder then visits the cells around it ring by ring and stops
     // as soon as everything closer than its pruning radius has been seen, instead of testing all n objects.
     bool use_grid = false;
-    if (p.grid) {
+    if (!GLOBAL && p.grid) {
         if (tid < 8) gred[tid] = (tid < 3) ? 0xffffffffu : 0u;
         for (int c = tid; c < kGridCells; c += kEmdThreads) cell_fill[c] = 0;
         __syncthreads();
@@ -540,7 +564,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         // rr, every unvisited object is at least rr cells away along some axis, i.e. farther than `covered`; once that is
         // at least the pruning radius R = 3 - better + 2e-6 (an object can change the top two only if sqrt(s) < R, prices
         // being >= 0) nothing unvisited can matter and the scan stops -- the same exact cut-off as the full scan below.
-        const bool grid_now = use_grid && total_u >= p.grid_min_u;
+        const bool grid_now = !GLOBAL && use_grid && total_u >= p.grid_min_u;
         if (grid_now) {
             int *next_bidder = reinterpret_cast<int *>(gred + 7);
             if (tid == 0) *next_bidder = 0;
@@ -554,7 +578,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 if (S > 1) {
                     while (hr < S - 1 && a >= ucount[hr]) { a -= ucount[hr]; ++hr; }
                 }
-                const int jl = *(cluster.map_shared_rank(list, hr) + a);
+                const int jl = *(rmt(list, hr) + a);
                 const int j = hr * ns + jl;
                 const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
                 const int bcx = min(kGridG - 1, max(0, (int)((x1 - gbox[0]) * gbox[3])));
@@ -660,11 +684,11 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 }
                 if (lane == 0) {
                     const float inc = __fadd_rn(__fsub_rn(m.best, m.better), p.eps);
-                    *(cluster.map_shared_rank(bid, hr) + jl) = m.idx;
-                    *(cluster.map_shared_rank(bid_inc, hr) + jl) = inc;
+                    *(rmt(bid, hr) + jl) = m.idx;
+                    *(rmt(bid_inc, hr) + jl) = inc;
                     if (m.idx >= 0) {
                         const int orank = m.idx / ns;
-                        atomic_max_float(cluster.map_shared_rank(max_inc, orank) + (m.idx - orank * ns), inc);
+                        atomic_max_float(rmt(max_inc, orank) + (m.idx - orank * ns), inc);
                     }
                 }
             }
@@ -686,11 +710,11 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             if (S > 1) {
                 while (hr < S - 1 && a >= ucount[hr]) { a -= ucount[hr]; ++hr; }
             }
-            const int jl = *(cluster.map_shared_rank(list, hr) + a);   // idle groups look at the first bidder of the share
+            const int jl = *(rmt(list, hr) + a);   // idle groups look at the first bidder of the share
             const int j = hr * ns + jl;
             const float x1 = x1g[j * 3 + 0], y1 = x1g[j * 3 + 1], z1 = x1g[j * 3 + 2];
             const int wl = tpb < 32 ? tpb : 32;
-            Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
+            Top2 r = scan_bidder<GLOBAL>(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
             if (wl == 32) warp_top2_redux(r);   // whole warp, one bidder: three redux.sync instead of five shuffle rounds
             else warp_merge_top2(r, wl);
             if (tpb > 32) {  // bidder groups span several warps: finish through shared memory
@@ -704,11 +728,11 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
             if (valid && t == 0) {
                 const float inc = __fadd_rn(__fsub_rn(r.best, r.better), p.eps);
-                *(cluster.map_shared_rank(bid, hr) + jl) = r.idx;
-                *(cluster.map_shared_rank(bid_inc, hr) + jl) = inc;
+                *(rmt(bid, hr) + jl) = r.idx;
+                *(rmt(bid_inc, hr) + jl) = inc;
                 if (r.idx >= 0) {
                     const int orank = r.idx / ns;
-                    atomic_max_float(cluster.map_shared_rank(max_inc, orank) + (r.idx - orank * ns), inc);
+                    atomic_max_float(rmt(max_inc, orank) + (r.idx - orank * ns), inc);
                 }
             }
         }
@@ -721,8 +745,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             if (o >= 0) {
                 const int orank = o / ns, ol = o - orank * ns;
                 const double bi = (double)bid_inc[jl];
-                const double mi = (double)*(cluster.map_shared_rank(max_inc, orank) + ol);
-                if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMin(cluster.map_shared_rank(winner, orank) + ol, base + jl);
+                const double mi = (double)*(rmt(max_inc, orank) + ol);
+                if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMin(rmt(winner, orank) + ol, base + jl);
             }
         }
         cluster.sync();  // [B]
@@ -733,21 +757,22 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             const int o = bid[jl];
             if (o >= 0) {
                 const int orank = o / ns, ol = o - orank * ns;
-                const int w = *(cluster.map_shared_rank(winner, orank) + ol);
+                const int w = *(rmt(winner, orank) + ol);
                 if (last || w == base + jl) {
                     const float inc = bid_inc[jl];
-                    int *inv = cluster.map_shared_rank(ass_inv, orank) + ol;
+                    int *inv = rmt(ass_inv, orank) + ol;
                     const int old = *inv;
                     if (!last && old != -1) {
                         const int hr = old / ns;
-                        *(cluster.map_shared_rank(assign, hr) + (old - hr * ns)) = -1;
+                        *(rmt(assign, hr) + (old - hr * ns)) = -1;
                     }
                     *inv = base + jl;
                     assign[jl] = o;
-                    const float np = __fadd_rn(price[o], inc);
-                    for (int r2 = 0; r2 < S; ++r2) *(cluster.map_shared_rank(price, r2) + o) = np;
-                    *(cluster.map_shared_rank(max_inc, orank) + ol) = kNegInit;
-                    *(cluster.map_shared_rank(winner, orank) + ol) = INT_MAX;
+                    const float np = __fadd_rn(ld1<GLOBAL>(price + o), inc);
+                    if (GLOBAL) price[o] = np;
+                    else for (int r2 = 0; r2 < S; ++r2) *(cluster.map_shared_rank(price, r2) + o) = np;
+                    *(rmt(max_inc, orank) + ol) = kNegInit;
+                    *(rmt(winner, orank) + ol) = INT_MAX;
                 }
             }
         }
@@ -756,10 +781,10 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         // a cloud is down to a handful of bidders it stays there -- typically for hundreds of iterations at the training
         // setting (eps = 0.05, 3000 iterations).  Those iterations are pure latency in the cluster-wide form (three cluster
         // barriers, remote atomics, a 1024-thread scan for one bidder): rank 0 finishes them alone.
-        if (p.solo && total_u <= kSoloMax && !last) { solo_from = it + 1; break; }
+        if (!GLOBAL && p.solo && total_u <= kSoloMax && !last) { solo_from = it + 1; break; }
     }
 
-    if (solo_from >= 0) {
+    if (!GLOBAL && solo_from >= 0) {
         {   // gather the sliced state and the unassigned points in rank 0
             float *r_maxinc = cluster.map_shared_rank(F_maxinc, 0);
             int *r_winner = cluster.map_shared_rank(F_winner, 0), *r_inv = cluster.map_shared_rank(F_inv, 0);
@@ -794,7 +819,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                     const bool valid = g < u;
                     const int j = lst[valid ? g : 0];
                     const float x1 = F_x1[j * 3 + 0], y1 = F_x1[j * 3 + 1], z1 = F_x1[j * 3 + 2];
-                    Top2 r = scan_bidder(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
+                    Top2 r = scan_bidder<GLOBAL>(ox, oy, oz, price, n, x1, y1, z1, tpb, t, valid);
                     warp_top2_redux(r);
                     if (wpb > 1) {   // the group's warps meet in shared memory; its first warp merges them
                         if (lane == 0) { w_best[warp] = r.best; w_better[warp] = r.better; w_idx[warp] = r.idx; }
@@ -886,11 +911,13 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 cur ^= 1;
             }
             // CalcDist + write-back for the whole cloud
+            float lsum = 0.f;
             for (int j = tid; j < n; j += kEmdThreads) {
                 const int o = F_assign[j];
                 float d = 0.f;
                 if (o >= 0)
                     d = sqdist_exact(x1g[j * 3 + 0] - ox[o], x1g[j * 3 + 1] - oy[o], x1g[j * 3 + 2] - oz[o]);
+                lsum += __fsqrt_rn(d);
                 p.dist[cb + j] = d;
                 p.assignment[cb + j] = o;
                 if (p.assignment_inv) p.assignment_inv[cb + j] = F_inv[j];
@@ -899,18 +926,25 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 if (p.bid_increments) p.bid_increments[cb + j] = F_binc[j];
                 if (p.price) p.price[cb + j] = price[j];
             }
+            if (p.loss_sums) {   // fused sum_j sqrt(dist) of Loss.get_emd_loss (loss/loss.py:25): one atomic per warp
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o2);
+                if (lane == 0) atomicAdd(p.loss_sums + cloud, lsum);
+            }
         }
         cluster.sync();  // keep every CTA's shared memory alive until rank 0 is done
         return;
     }
 
     // ---- CalcDist (emd_cuda.cu:217-226) + write-back of the state the reference leaves in its tensors
+    float lsum = 0.f;
     for (int k = tid; k < ns; k += kEmdThreads) {
         const int j = base + k;
         const int o = assign[k];
         float d = 0.f;
         if (o >= 0)
             d = sqdist_exact(x1g[j * 3 + 0] - ox[o], x1g[j * 3 + 1] - oy[o], x1g[j * 3 + 2] - oz[o]);
+        lsum += __fsqrt_rn(d);
         p.dist[cb + j] = d;
         p.assignment[cb + j] = o;
         if (p.assignment_inv) p.assignment_inv[cb + j] = ass_inv[k];
@@ -919,24 +953,56 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         if (p.bid_increments) p.bid_increments[cb + j] = bid_inc[k];
         if (p.price) p.price[cb + j] = price[j];
     }
+    if (p.loss_sums) {   // fused sum_j sqrt(dist) of Loss.get_emd_loss (loss/loss.py:25): one atomic per warp
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o2);
+        if (lane == 0) atomicAdd(p.loss_sums + cloud, lsum);
+    }
     cluster.sync();  // keep every CTA's shared memory alive until all remote accesses are done
 }
 
 // emd_cuda_backward's NmDistanceGradKernel (emd_cuda.cu:284-300): one term per address.
-__global__ void __launch_bounds__(256) emd_grad_kernel(int total, int n, const float *__restrict__ xyz1,
+// OVERWRITE = false: the reference's contract (accumulate into the caller-zeroed gradient); true: plain store.
+// MEAN_LOSS: grad_dist is formed in the kernel for loss = sqrt(dist).mean(1).mean() (loss/loss.py:25) from the saved
+// distances: grad_dist = ((upstream / B) / n) / (2 sqrt(dist)) -- autograd's own sequence (mean, mean(1), sqrt), including
+// the infinite factor at dist == 0 that the reference's loss has.
+template <bool OVERWRITE, bool MEAN_LOSS>
+__global__ void __launch_bounds__(256) emd_grad_kernel(int total, int n, int b, const float *__restrict__ xyz1,
                                                        const float *__restrict__ xyz2, const float *__restrict__ grad_dist,
-                                                       const int *__restrict__ idx, float *grad_xyz) {
+                                                       const float *__restrict__ upstream, const int *__restrict__ idx,
+                                                       float *grad_xyz) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int cloud = e / n;
     const int j2 = idx[e];
-    const float g = grad_dist[e] * 2.0f;
+    float gd;
+    if (MEAN_LOSS) {
+        const float up = upstream ? __ldg(upstream) : 1.0f;
+        const float t = __fdiv_rn(__fdiv_rn(up, (float)b), (float)n);
+        gd = __fdiv_rn(t, __fmul_rn(2.0f, __fsqrt_rn(grad_dist[e])));   // grad_dist carries the saved dist here
+    } else {
+        gd = grad_dist[e];
+    }
+    const float g = gd * 2.0f;
     const float *a = xyz1 + (size_t)e * 3;
-    const float *bq = xyz2 + ((size_t)cloud * n + j2) * 3;
     float *o = grad_xyz + (size_t)e * 3;
-    o[0] = __fadd_rn(o[0], __fmul_rn(g, __fsub_rn(a[0], bq[0])));
-    o[1] = __fadd_rn(o[1], __fmul_rn(g, __fsub_rn(a[1], bq[1])));
-    o[2] = __fadd_rn(o[2], __fmul_rn(g, __fsub_rn(a[2], bq[2])));
+    float v[3] = {0.f, 0.f, 0.f};
+    if (j2 >= 0) {   // an unassigned point (possible when iters == 0) has no term
+        const float *bq = xyz2 + ((size_t)cloud * n + j2) * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = __fmul_rn(g, __fsub_rn(a[k], bq[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = OVERWRITE ? v[k] : __fadd_rn(o[k], v[k]);
+}
+
+// loss = mean_b( sum_j sqrt(dist[b, j]) / n ) from the per-cloud sums of the auction kernel's epilogue; one warp.
+__global__ void emd_mean_loss_kernel(const float *__restrict__ sums, int b, float n, float *__restrict__ out) {
+    float s1 = 0.f;
+    for (int i = threadIdx.x; i < b; i += 32) s1 += __fdiv_rn(sums[i], n);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    if (threadIdx.x == 0) *out = __fdiv_rn(s1, (float)b);
 }
 
 static size_t emd_smem_bytes(int n, int S) {
@@ -950,44 +1016,61 @@ static size_t emd_solo_bytes(int n) { return sizeof(float) * ((size_t)9 * n + 2 
 
 using namespace psd;
 
-static int g_emd_grid = 1;
-int psd_set_emd_grid(int enable) { const int old = g_emd_grid; if (enable == 0 || enable == 1) g_emd_grid = enable; return old; }
-static int g_emd_solo = 1;
-int psd_set_emd_solo(int enable) { const int old = g_emd_solo; if (enable == 0 || enable == 1) g_emd_solo = enable; return old; }
+static std::atomic<int> g_emd_grid{1};
+int psd_set_emd_grid(int enable) { return (enable == 0 || enable == 1) ? g_emd_grid.exchange(enable) : g_emd_grid.load(); }
+static std::atomic<int> g_emd_solo{1};
+int psd_set_emd_solo(int enable) { return (enable == 0 || enable == 1) ? g_emd_solo.exchange(enable) : g_emd_solo.load(); }
 
-// returns cudaSuccess, or an error; *unsupported is set when the shape does not fit the persistent kernel
+// returns cudaSuccess, or an error.  Clouds whose state fits in the (distributed) shared memory of a cluster (n <= 8192) run
+// the resident kernel; larger clouds run the same auction on a stream-ordered global workspace (11 n floats per cloud).
+// force_cluster: 0 = automatic, 1/2/4/8 = cluster size (test hook), negative = -cluster size AND the global-workspace form
+// (test hook: parity of the GLOBAL mode at small sizes).
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                                    float *price, int *assignment_inv, int *bid, float *bid_increments,
                                    float *max_increments, float eps, int iters, int force_cluster, int fresh,
-                                   cudaStream_t stream, int *unsupported) {
+                                   float *loss_sums, cudaStream_t stream, int *unsupported) {
     *unsupported = 0;
     if (b <= 0 || n <= 0) return cudaSuccess;
     int dev = 0, num_sms = 148, max_smem = 227 * 1024;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    bool global = force_cluster < 0;
     int S = 1;
-    if (force_cluster > 0) {
-        S = force_cluster;
+    if (force_cluster != 0) {
+        S = force_cluster < 0 ? -force_cluster : force_cluster;
+        if (S != 1 && S != 2 && S != 4 && S != 8) return cudaErrorInvalidValue;
     } else {
         while (S < 8 && b * (S * 2) <= num_sms) S *= 2;
     }
-    while (S < 8 && emd_smem_bytes(n, S) > (size_t)max_smem) S *= 2;
-    if (emd_smem_bytes(n, S) > (size_t)max_smem || (n % S) != 0) { *unsupported = 1; return cudaSuccess; }
-    size_t smem = emd_smem_bytes(n, S);
-    const int grid = (smem + emd_grid_bytes(n) <= (size_t)max_smem && g_emd_grid) ? 1 : 0;
-    if (grid) smem += emd_grid_bytes(n);
-    const int solo = (smem + emd_solo_bytes(n) <= (size_t)max_smem && g_emd_solo) ? 1 : 0;
-    if (solo) smem += emd_solo_bytes(n);
-    cudaError_t e = cudaFuncSetAttribute(emd_auction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (!global) {
+        while (S < 8 && emd_smem_bytes(n, S) > (size_t)max_smem) S *= 2;
+        if (emd_smem_bytes(n, S) > (size_t)max_smem) { global = true; S = 8; }
+    }
+    if ((n % S) != 0) { *unsupported = 1; return cudaSuccess; }
     EmdParams p;
     p.xyz1 = xyz1; p.xyz2 = xyz2; p.dist = dist; p.assignment = assignment; p.price = price;
     p.assignment_inv = assignment_inv; p.max_increments = max_increments; p.bid = bid; p.bid_increments = bid_increments;
-    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = solo; p.grid = grid;
+    p.b = b; p.n = n; p.eps = eps; p.iters = iters; p.fresh = fresh; p.solo = 0; p.grid = 0; p.gws = nullptr;
+    p.loss_sums = loss_sums;
     {
         const char *ev = getenv("PSD_EMD_GRID_MIN_U");
         p.grid_min_u = ev ? atoi(ev) : 144;   // measured optimum for cluster sizes 2, 4 and 8 (sweep 0 ... 1024 at B = 64, 32, 8)
+    }
+    size_t smem;
+    cudaError_t e;
+    if (global) {
+        smem = sizeof(float) * (32 * 3 + 8 + 4);
+        e = cudaMallocAsync(reinterpret_cast<void **>(&p.gws), sizeof(float) * 11 * (size_t)n * (size_t)b, stream);
+        if (e != cudaSuccess) return e;
+    } else {
+        smem = emd_smem_bytes(n, S);
+        p.grid = (smem + emd_grid_bytes(n) <= (size_t)max_smem && g_emd_grid.load()) ? 1 : 0;
+        if (p.grid) smem += emd_grid_bytes(n);
+        p.solo = (smem + emd_solo_bytes(n) <= (size_t)max_smem && g_emd_solo.load()) ? 1 : 0;
+        if (p.solo) smem += emd_solo_bytes(n);
+        e = cudaFuncSetAttribute(emd_auction_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned int)(b * S));
@@ -1001,13 +1084,28 @@ cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, emd_auction_kernel, p);
+    if (global) {
+        e = cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p);
+        const cudaError_t e2 = cudaFreeAsync(p.gws, stream);
+        return e != cudaSuccess ? e : e2;
+    }
+    return cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p);
 }
 
+cudaError_t psd_launch_emd_mean_loss(const float *sums, int b, int n, float *out, cudaStream_t stream) {
+    emd_mean_loss_kernel<<<1, 32, 0, stream>>>(sums, b, (float)n, out);
+    return cudaGetLastError();
+}
+
+// mode: 0 = accumulate grad_dist terms (reference contract), 1 = overwrite, 2 = mean-loss gradient (graddist = saved dist,
+// upstream = device scalar or NULL for 1.0), overwrite
 cudaError_t psd_launch_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
-                                    const int *idx, int b, int n, cudaStream_t stream) {
+                                    const int *idx, int b, int n, int mode, const float *upstream, cudaStream_t stream) {
     if (b <= 0 || n <= 0) return cudaSuccess;
     const int total = b * n;
-    emd_grad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(total, n, xyz1, xyz2, graddist, idx, gradxyz);
+    const int blocks = (total + 255) / 256;
+    if (mode == 0) emd_grad_kernel<false, false><<<blocks, 256, 0, stream>>>(total, n, b, xyz1, xyz2, graddist, nullptr, idx, gradxyz);
+    else if (mode == 1) emd_grad_kernel<true, false><<<blocks, 256, 0, stream>>>(total, n, b, xyz1, xyz2, graddist, nullptr, idx, gradxyz);
+    else emd_grad_kernel<true, true><<<blocks, 256, 0, stream>>>(total, n, b, xyz1, xyz2, graddist, upstream, idx, gradxyz);
     return cudaGetLastError();
 }

@@ -90,12 +90,9 @@ cudaError_t psd_launch_proj_min_dist(const float *pred, const float *gt, const f
         const int hw = h * w;
         const size_t smem = 2 * sizeof(float) * (size_t)hw;
         if (smem > 200 * 1024) return cudaErrorInvalidValue;
-        static bool attr = false;
-        if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(proj_min_dist_intended_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (e != cudaSuccess) return e;
-            attr = true;
-        }
+        // the opt-in applies per device: set it on every launch (cheap next to this kernel; emd.cu and fps.cu do the same)
+        cudaError_t e = cudaFuncSetAttribute(proj_min_dist_intended_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
         const int qblocks = (hw + 255) / 256;
         proj_min_dist_intended_kernel<<<(unsigned)(b * 2 * qblocks), 256, smem, stream>>>(pred, gt, table, b, h, w, out_min, out_inv);
     }

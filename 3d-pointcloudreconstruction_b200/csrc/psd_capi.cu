@@ -5,6 +5,7 @@
 
 #include "../../include/psd_b200.h"
 #include "psd_common.cuh"
+#include "psd_device.h"
 
 // launchers implemented in chamfer.cu / emd.cu
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
@@ -12,7 +13,8 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
                                        int *fs_count, int q_begin, int q_count, cudaStream_t stream);
 cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
-                                        int b, int n, int m, cudaStream_t stream, const float *upstream = nullptr);
+                                        int b, int n, int m, int layout, int overwrite, cudaStream_t stream,
+                                        const float *upstream = nullptr);
 cudaError_t psd_launch_chamfer_mean_loss(const float *sums, int b, int n, int m, float *out, cudaStream_t stream);
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset);
 int psd_set_nn_variant(int v);
@@ -26,6 +28,8 @@ int psd_set_emd_grid(int enable);
 int psd_set_tc_max_ctas(int n);
 cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
                                  cudaStream_t stream);
+cudaError_t psd_launch_cont_proj_backward(const float *pcl, const float *gout, int b, int n, int grid_h, int grid_w,
+                                          float sigma_sq, float *gpcl, cudaStream_t stream);
 cudaError_t psd_launch_fps(const float *xyz, int b, int n, int npoint, int start, long long *centroids, cudaStream_t stream);
 int psd_fps_max_points();
 cudaError_t psd_launch_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode,
@@ -35,11 +39,36 @@ void psd_set_tc_prof(long long *prof);
 cudaError_t psd_launch_emd_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                                    float *price, int *assignment_inv, int *bid, float *bid_increments,
                                    float *max_increments, float eps, int iters, int force_cluster, int fresh,
-                                   cudaStream_t stream, int *unsupported);
+                                   float *loss_sums, cudaStream_t stream, int *unsupported);
+cudaError_t psd_launch_emd_mean_loss(const float *sums, int b, int n, float *out, cudaStream_t stream);
 cudaError_t psd_launch_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist,
-                                    const int *idx, int b, int n, cudaStream_t stream);
+                                    const int *idx, int b, int n, int mode, const float *upstream, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
+
+namespace psd {
+static std::mutex g_state_mutex;
+static DeviceState g_devices[kMaxDevices];
+std::mutex &state_mutex() { return g_state_mutex; }
+DeviceState *device_state(cudaError_t *err) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && (dev < 0 || dev >= kMaxDevices)) e = cudaErrorInvalidDevice;
+    if (e != cudaSuccess) { if (err) *err = e; return nullptr; }
+    DeviceState *ds = &g_devices[dev];
+    std::lock_guard<std::mutex> lock(g_state_mutex);
+    if (!ds->init) {
+        e = cudaDeviceGetAttribute(&ds->num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ds->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) { if (err) *err = e; return nullptr; }
+        ds->device = dev;
+        ds->init = true;
+    }
+    return ds;
+}
+}  // namespace psd
+using psd::DeviceState;
+using psd::kStepSlots;
 
 void psd_set_error(const char *what, cudaError_t err) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(err));
@@ -71,8 +100,8 @@ int psd_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int 
 int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
                            float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, int q_begin,
                            int q_count, void *stream) {
-    if (layout != 0 && layout != 1) {
-        psd_set_error_msg("psd_chamfer_forward_ex: layout must be 0 ([B,N,3]) or 1 ([B,3,N])");
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_forward_ex: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
         return -1;
     }
     return finish("psd_chamfer_forward_ex",
@@ -85,8 +114,22 @@ int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, 
                          int m, void *stream) {
     return finish("psd_chamfer_backward",
                   psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2, b, n, m,
-                                              (cudaStream_t)stream));
+                                              0, 0, (cudaStream_t)stream));
 }
+
+int psd_chamfer_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                            const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
+                            int m, int layout, int overwrite, void *stream) {
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_backward_ex: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
+        return -1;
+    }
+    return finish("psd_chamfer_backward_ex",
+                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2, b, n, m,
+                                              layout, overwrite != 0, (cudaStream_t)stream));
+}
+
+static const char *kEmdShapeMsg = "the cloud size must be a multiple of the cluster size";
 
 int psd_emd_forward(const float *xyz1, const float *xyz2, int b, int n, int m, float *dist, int *assignment,
                     float *price, int *assignment_inv, int *bid, float *bid_increments, float *max_increments,
@@ -99,22 +142,20 @@ int psd_emd_forward(const float *xyz1, const float *xyz2, int b, int n, int m, f
     if (n % 1024 != 0) { psd_set_error_msg("Input Error! The size of the point clouds should be a multiple of 1024."); return -1; }
     int unsupported = 0;
     cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, price, assignment_inv, bid, bid_increments,
-                                           max_increments, eps, iters, 0, 0, (cudaStream_t)stream, &unsupported);
-    if (unsupported) {
-        psd_set_error_msg("psd_emd_forward: n too large for the shared-memory resident auction (n <= 8192 supported)");
-        return 0;
-    }
+                                           max_increments, eps, iters, 0, 0, nullptr, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg(kEmdShapeMsg); return 0; }
     return finish("psd_emd_forward", e);
 }
 
-// test hook: force the cluster size (1,2,4,8) so that every decomposition can be parity-checked
+// test hook: force the cluster size (1,2,4,8; negative = the same size on the global-workspace form of the kernel) so that
+// every decomposition can be parity-checked
 int psd_emd_forward_cluster(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                             float *price, int *assignment_inv, float eps, int iters, int cluster_size, void *stream) {
     if (b > 512 || n % 1024 != 0) return -1;
     int unsupported = 0;
     cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, price, assignment_inv, nullptr, nullptr,
-                                           nullptr, eps, iters, cluster_size, 0, (cudaStream_t)stream, &unsupported);
-    if (unsupported) { psd_set_error_msg("psd_emd_forward_cluster: shape does not fit"); return 0; }
+                                           nullptr, eps, iters, cluster_size, 0, nullptr, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg(kEmdShapeMsg); return 0; }
     return finish("psd_emd_forward_cluster", e);
 }
 
@@ -124,20 +165,44 @@ int psd_emd_forward_fresh(const float *xyz1, const float *xyz2, int b, int n, fl
     if (n % 1024 != 0) { psd_set_error_msg("Input Error! The size of the point clouds should be a multiple of 1024."); return -1; }
     int unsupported = 0;
     cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                           eps, iters, 0, 1, (cudaStream_t)stream, &unsupported);
-    if (unsupported) { psd_set_error_msg("psd_emd_forward_fresh: n too large for the shared-memory resident auction (n <= 8192 supported)"); return 0; }
+                                           eps, iters, 0, 1, nullptr, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg(kEmdShapeMsg); return 0; }
     return finish("psd_emd_forward_fresh", e);
 }
 
 int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
                      int b, int n, void *stream) {
-    return finish("psd_emd_backward", psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, (cudaStream_t)stream));
+    return finish("psd_emd_backward", psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, 0, nullptr, (cudaStream_t)stream));
+}
+
+int psd_emd_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
+                        int b, int n, int overwrite, void *stream) {
+    return finish("psd_emd_backward_ex",
+                  psd_launch_emd_backward(xyz1, xyz2, gradxyz, graddist, idx, b, n, overwrite ? 1 : 0, nullptr, (cudaStream_t)stream));
+}
+
+int psd_emd_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment, float eps,
+                              int iters, float *sums_zeroed, float *loss, void *stream) {
+    if (b > 512) { psd_set_error_msg("Input Error! The batch size should be less than 512."); return -1; }
+    if (n % 1024 != 0) { psd_set_error_msg("Input Error! The size of the point clouds should be a multiple of 1024."); return -1; }
+    int unsupported = 0;
+    cudaError_t e = psd_launch_emd_forward(xyz1, xyz2, b, n, dist, assignment, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                           eps, iters, 0, 1, sums_zeroed, (cudaStream_t)stream, &unsupported);
+    if (unsupported) { psd_set_error_msg(kEmdShapeMsg); return 0; }
+    if (e == cudaSuccess) e = psd_launch_emd_mean_loss(sums_zeroed, b, n, loss, (cudaStream_t)stream);
+    return finish("psd_emd_mean_loss_forward", e);
+}
+
+int psd_emd_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, const float *dist, const int *assignment,
+                               const float *upstream, int b, int n, void *stream) {
+    return finish("psd_emd_mean_loss_backward",
+                  psd_launch_emd_backward(xyz1, xyz2, gradxyz1, dist, assignment, b, n, 2, upstream, (cudaStream_t)stream));
 }
 
 int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
                                   float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, void *stream) {
-    if (layout != 0 && layout != 1) {
-        psd_set_error_msg("psd_chamfer_mean_loss_forward: layout must be 0 ([B,N,3]) or 1 ([B,3,N])");
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_mean_loss_forward: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
         return -1;
     }
     cudaError_t e = psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums_zeroed, 0.f, nullptr,
@@ -149,8 +214,20 @@ int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, i
 int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                    const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream) {
     return finish("psd_chamfer_mean_loss_backward",
-                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, nullptr, nullptr, idx1, idx2, b, n, m,
+                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, nullptr, nullptr, idx1, idx2, b, n, m, 0, 0,
                                               (cudaStream_t)stream, upstream));
+}
+
+int psd_chamfer_mean_loss_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                      const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, int layout,
+                                      int overwrite, void *stream) {
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_mean_loss_backward_ex: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
+        return -1;
+    }
+    return finish("psd_chamfer_mean_loss_backward_ex",
+                  psd_launch_chamfer_backward(xyz1, xyz2, gradxyz1, gradxyz2, nullptr, nullptr, idx1, idx2, b, n, m, layout,
+                                              overwrite != 0, (cudaStream_t)stream, upstream));
 }
 
 int psd_proj_min_dist(const float *pred, const float *gt, const float *table, int b, int h, int w, int mode, float *min_dist,
@@ -178,6 +255,17 @@ int psd_farthest_point_sample(const float *xyz, int b, int n, int npoint, int st
 int psd_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out, void *stream) {
     if (b < 0 || n < 0 || grid_h < 1 || grid_w < 1) { psd_set_error_msg("psd_cont_proj: b, n >= 0 and grid_h, grid_w >= 1 required"); return -1; }
     return finish("psd_cont_proj", psd_launch_cont_proj(pcl, b, n, grid_h, grid_w, sigma_sq, out, (cudaStream_t)stream));
+}
+
+int psd_cont_proj_backward(const float *pcl, const float *grad_out, int b, int n, int grid_h, int grid_w, float sigma_sq,
+                           float *grad_pcl, void *stream) {
+    if (b < 0 || n < 0 || grid_h < 1 || grid_w < 1) { psd_set_error_msg("psd_cont_proj_backward: b, n >= 0 and grid_h, grid_w >= 1 required"); return -1; }
+    if (sizeof(float) * ((size_t)grid_h * (grid_w + 1) + 8 * (size_t)(grid_h + grid_w)) > 200 * 1024 || b > 65535) {
+        psd_set_error_msg("psd_cont_proj_backward: the gradient image must fit in shared memory (about 220 x 220) and b <= 65535");
+        return -1;
+    }
+    return finish("psd_cont_proj_backward",
+                  psd_launch_cont_proj_backward(pcl, grad_out, b, n, grid_h, grid_w, sigma_sq, grad_pcl, (cudaStream_t)stream));
 }
 
 int psd_nn_f64(const void *src, const void *dst, int in_f64, int batch, int n_src, int n_dst, double *distances, int *indices,
@@ -217,26 +305,28 @@ int psd_chamfer_stats(long long *out_host2, int reset) {
     return 1;
 }
 
-// ---- host-buffer entry point: stage through a grow-only device workspace owned by the library
-// (two workspaces: forward-only and training-step)
-static float *g_ws = nullptr;
-static size_t g_ws_bytes = 0;
+// ---- host-buffer entry points: stage through grow-only device workspaces owned by the library, one set per device
+// (forward-only, and kStepSlots training-step workspaces).  One mutex serialises the bookkeeping of concurrent callers.
+static std::mutex g_host_api_mutex;
 
 int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *dist1_host,
                              float *dist2_host, int *idx1_host, int *idx2_host, void *stream_) {
+    std::lock_guard<std::mutex> api_lock(g_host_api_mutex);
     cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e = cudaSuccess;
+    DeviceState *ds = psd::device_state(&e);
+    if (ds == nullptr) return finish("psd_chamfer_forward_host(device)", e);
     const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
     const size_t need = sizeof(float) * (3 * s1 + 3 * s2 + 2 * s1 + 2 * s2);
-    if (need > g_ws_bytes) {
-        if (g_ws) cudaFree(g_ws);
-        g_ws = nullptr; g_ws_bytes = 0;
-        cudaError_t e = cudaMalloc(&g_ws, need);
+    if (need > ds->fwd_ws_bytes) {
+        if (ds->fwd_ws) { cudaDeviceSynchronize(); cudaFree(ds->fwd_ws); }
+        ds->fwd_ws = nullptr; ds->fwd_ws_bytes = 0;
+        e = cudaMalloc(&ds->fwd_ws, need);
         if (e != cudaSuccess) return finish("psd_chamfer_forward_host(cudaMalloc)", e);
-        g_ws_bytes = need;
+        ds->fwd_ws_bytes = need;
     }
-    float *d_x1 = g_ws, *d_x2 = d_x1 + 3 * s1, *d_d1 = d_x2 + 3 * s2, *d_d2 = d_d1 + s1;
+    float *d_x1 = ds->fwd_ws, *d_x2 = d_x1 + 3 * s1, *d_d1 = d_x2 + 3 * s2, *d_d2 = d_d1 + s1;
     int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
-    cudaError_t e;
     if ((e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_x2, xyz2_host, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
         return finish("psd_chamfer_forward_host(H2D)", e);
@@ -251,15 +341,20 @@ int psd_chamfer_forward_host(const float *xyz1_host, const float *xyz2_host, int
 }
 
 
-// fwd + fused mean loss + bwd of one training step with HOST inputs: the end-to-end form of Loss.get_chamfer_loss
-// (loss/loss.py:30-37) followed by loss.backward().  Gradients stay on the device unless host pointers are given.
-static const int kStepSlots = 8;
-static float *g_ws2[kStepSlots] = {};
-static size_t g_ws2_bytes[kStepSlots] = {};
+// fwd + fused mean loss + bwd of one training step: the end-to-end form of Loss.get_chamfer_loss (loss/loss.py:30-37)
+// followed by loss.backward().  Gradients stay on the device unless host pointers are given.
+struct StepArgs {
+    const float *x1 = nullptr, *x2 = nullptr;   // xyz1: host, or device when x1_dev; xyz2: host
+    bool x1_dev = false;                        // the prediction is already on the device (the generator's output, train.py:160)
+    int layout1 = 0;                            // 1: the device prediction is [B,3,N] (the generator's native layout)
+    int b = 0, n = 0, m = 0;
+    float *loss_host = nullptr, *g1_host = nullptr, *g2_host = nullptr;
+    float *g1_user = nullptr;                   // x1_dev: device buffer that receives d loss / d xyz1 (same layout as xyz1)
+};
 
-// One training step's stream work (H2D, memsets, forward, mean loss, backward, D2H) for a given workspace.
-static cudaError_t enqueue_loss_step(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
-                                     float *gradxyz1_host, float *gradxyz2_host, float *ws, cudaStream_t stream) {
+// One training step's stream work (H2D, forward, mean loss, backward, D2H) for a given workspace.
+static cudaError_t enqueue_loss_step(const StepArgs &a, float *ws, cudaStream_t stream) {
+    const int b = a.b, n = a.n, m = a.m;
     const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
     // layout: xyz1 | xyz2 | grad1 | grad2 | dist1 | dist2 | idx1 | idx2 | sums[2b] | loss
     float *d_x1 = ws, *d_x2 = d_x1 + 3 * s1, *d_g1 = d_x2 + 3 * s2, *d_g2 = d_g1 + 3 * s1;
@@ -267,40 +362,45 @@ static cudaError_t enqueue_loss_step(const float *xyz1_host, const float *xyz2_h
     int *d_i1 = reinterpret_cast<int *>(d_d2 + s2), *d_i2 = d_i1 + s1;
     float *d_sums = reinterpret_cast<float *>(d_i2 + s2), *d_loss = d_sums + 2 * (size_t)b;
     cudaError_t e;
-    // the two clouds are adjacent in the workspace: one copy when they are adjacent on the host too
-    if (xyz2_host == xyz1_host + 3 * s1) {
-        e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * (s1 + s2), cudaMemcpyHostToDevice, stream);
+    const float *x1 = d_x1;
+    float *g1 = d_g1;
+    int layout = 0;
+    if (a.x1_dev) {
+        // only the ground truth travels: the prediction (and its gradient) are the caller's device tensors
+        x1 = a.x1; g1 = a.g1_user ? a.g1_user : d_g1; layout = a.layout1 ? 1 : 0;
+        e = cudaMemcpyAsync(d_x2, a.x2, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
+    } else if (a.x2 == a.x1 + 3 * s1) {
+        // the two clouds are adjacent in the workspace: one copy when they are adjacent on the host too
+        e = cudaMemcpyAsync(d_x1, a.x1, sizeof(float) * 3 * (s1 + s2), cudaMemcpyHostToDevice, stream);
     } else {
-        e = cudaMemcpyAsync(d_x1, xyz1_host, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x2, xyz2_host, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
+        e = cudaMemcpyAsync(d_x1, a.x1, sizeof(float) * 3 * s1, cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x2, a.x2, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
     }
     if (e != cudaSuccess) return e;
-    // gradients and per-cloud sums start from zero: one memset each (grad1|grad2 are adjacent)
-    if ((e = cudaMemsetAsync(d_g1, 0, sizeof(float) * 3 * (s1 + s2), stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(d_sums, 0, sizeof(float) * (2 * (size_t)b + 1), stream)) != cudaSuccess)
-        return e;
-    e = psd_launch_chamfer_forward(d_x1, d_x2, b, n, m, 0, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream);
+    // per-cloud sums start from zero; the gradients need no initialisation (two-phase backward)
+    if ((e = cudaMemsetAsync(d_sums, 0, sizeof(float) * (2 * (size_t)b + 1), stream)) != cudaSuccess) return e;
+    e = psd_launch_chamfer_forward(x1, d_x2, b, n, m, layout, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream);
     if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(d_sums, b, n, m, d_loss, stream);
-    if (e == cudaSuccess) e = psd_launch_chamfer_backward(d_x1, d_x2, d_g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, stream, nullptr);
+    if (e == cudaSuccess) e = psd_launch_chamfer_backward(x1, d_x2, g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, layout, 1, stream, nullptr);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && gradxyz1_host) e = cudaMemcpyAsync(gradxyz1_host, d_g1, sizeof(float) * 3 * s1, cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess && gradxyz2_host) e = cudaMemcpyAsync(gradxyz2_host, d_g2, sizeof(float) * 3 * s2, cudaMemcpyDeviceToHost, stream);
+    e = cudaMemcpyAsync(a.loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && a.g1_host) e = cudaMemcpyAsync(a.g1_host, g1, sizeof(float) * 3 * s1, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && a.g2_host) e = cudaMemcpyAsync(a.g2_host, d_g2, sizeof(float) * 3 * s2, cudaMemcpyDeviceToHost, stream);
     return e;
 }
 
 // A training loop calls the step with the same few pinned staging buffers over and over: the second time a
 // (buffers, shape, workspace) combination is seen its stream work is captured into a CUDA graph, and from then on one
-// cudaGraphLaunch replaces the nine API calls of a step (the host side, not the GPU, bounds a 40 µs step otherwise).
+// cudaGraphLaunch replaces the API calls of a step (the host side, not the GPU, bounds a 40 us step otherwise).
 struct StepGraph {
-    const void *x1 = nullptr, *x2 = nullptr, *loss = nullptr, *g1 = nullptr, *g2 = nullptr, *ws = nullptr;
-    int b = 0, n = 0, m = 0, variant = 0, device = -1, tc_ctas = 0;
+    const void *x1 = nullptr, *x2 = nullptr, *loss = nullptr, *g1 = nullptr, *g2 = nullptr, *g1u = nullptr, *ws = nullptr;
+    int b = 0, n = 0, m = 0, variant = 0, device = -1, tc_ctas = 0, flags = 0;
     cudaGraphExec_t exec = nullptr;
     bool plain = false;   // capture was not possible (pageable buffers, stream already capturing): keep the plain path
     unsigned long long last_use = 0;
     bool same(const StepGraph &o) const {
-        return x1 == o.x1 && x2 == o.x2 && loss == o.loss && g1 == o.g1 && g2 == o.g2 && ws == o.ws && b == o.b && n == o.n &&
-               m == o.m && variant == o.variant && device == o.device && tc_ctas == o.tc_ctas;
+        return x1 == o.x1 && x2 == o.x2 && loss == o.loss && g1 == o.g1 && g2 == o.g2 && g1u == o.g1u && ws == o.ws && b == o.b &&
+               n == o.n && m == o.m && variant == o.variant && device == o.device && tc_ctas == o.tc_ctas && flags == o.flags;
     }
 };
 static const int kStepGraphs = 64;
@@ -324,28 +424,32 @@ static bool pinned_host(const void *p) {
 }
 
 int psd_host_step_graphs(int enable) {
+    std::lock_guard<std::mutex> api_lock(g_host_api_mutex);
     const int old = g_step_graph_enabled;
     if (enable == 0 || enable == 1) g_step_graph_enabled = enable;
     return old;
 }
 
-int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
-                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
-                                  int slot, int sync, void *stream_) {
-    if (slot < 0 || slot >= kStepSlots) { psd_set_error_msg("psd_chamfer_loss_step_host_ex: slot must be 0..7"); return -1; }
+static int loss_step_common(const StepArgs &a, float **gradxyz1_dev, float **gradxyz2_dev, int slot, int sync, void *stream_) {
+    if (slot < 0 || slot >= kStepSlots) { psd_set_error_msg("psd_chamfer_loss_step: slot must be 0..7"); return -1; }
+    std::unique_lock<std::mutex> api_lock(g_host_api_mutex);
     cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e0 = cudaSuccess;
+    DeviceState *ds = psd::device_state(&e0);
+    if (ds == nullptr) return finish("psd_chamfer_loss_step(device)", e0);
+    const int b = a.b, n = a.n, m = a.m;
     const size_t s1 = (size_t)b * n, s2 = (size_t)b * m;
     const size_t nfloat = 6 * (s1 + s2) + 2 * (s1 + s2) + 2 * (size_t)b + 4;
     const size_t need = sizeof(float) * nfloat;
-    if (need > g_ws2_bytes[slot]) {
-        if (g_ws2[slot]) { cudaDeviceSynchronize(); drop_step_graphs(g_ws2[slot]); cudaFree(g_ws2[slot]); }
-        g_ws2[slot] = nullptr; g_ws2_bytes[slot] = 0;
-        cudaError_t e = cudaMalloc(&g_ws2[slot], need);
-        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(cudaMalloc)", e);
-        g_ws2_bytes[slot] = need;
+    if (need > ds->step_ws_bytes[slot]) {
+        if (ds->step_ws[slot]) { cudaDeviceSynchronize(); drop_step_graphs(ds->step_ws[slot]); cudaFree(ds->step_ws[slot]); }
+        ds->step_ws[slot] = nullptr; ds->step_ws_bytes[slot] = 0;
+        cudaError_t e = cudaMalloc(&ds->step_ws[slot], need);
+        if (e != cudaSuccess) return finish("psd_chamfer_loss_step(cudaMalloc)", e);
+        ds->step_ws_bytes[slot] = need;
     }
-    float *const ws = g_ws2[slot];
-    if (gradxyz1_dev) *gradxyz1_dev = ws + 3 * (s1 + s2);
+    float *const ws = ds->step_ws[slot];
+    if (gradxyz1_dev) *gradxyz1_dev = (a.x1_dev && a.g1_user) ? a.g1_user : ws + 3 * (s1 + s2);
     if (gradxyz2_dev) *gradxyz2_dev = ws + 3 * (s1 + s2) + 3 * s1;
 
     if (g_step_graph_enabled < 0) {
@@ -355,9 +459,10 @@ int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host
     bool launched = false;
     if (g_step_graph_enabled && stream != nullptr && stream != cudaStreamLegacy) {
         StepGraph key;
-        key.x1 = xyz1_host; key.x2 = xyz2_host; key.loss = loss_host; key.g1 = gradxyz1_host; key.g2 = gradxyz2_host;
+        key.x1 = a.x1; key.x2 = a.x2; key.loss = a.loss_host; key.g1 = a.g1_host; key.g2 = a.g2_host; key.g1u = a.g1_user;
         key.ws = ws; key.b = b; key.n = n; key.m = m; key.variant = psd_set_nn_variant(-1); key.tc_ctas = psd_set_tc_max_ctas(-1);
-        cudaGetDevice(&key.device);
+        key.flags = (a.x1_dev ? 1 : 0) | (a.layout1 ? 2 : 0);
+        key.device = ds->device;
         StepGraph *hit = nullptr, *victim = &g_step_graph[0];
         for (StepGraph &g : g_step_graph) {
             if (g.ws && g.same(key)) { hit = &g; break; }
@@ -370,14 +475,14 @@ int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host
         } else {
             hit->last_use = ++g_step_clock;
             if (hit->exec == nullptr && !hit->plain &&
-                !(pinned_host(xyz1_host) && pinned_host(xyz2_host) && pinned_host(loss_host) && pinned_host(gradxyz1_host) &&
-                  pinned_host(gradxyz2_host)))
+                !((a.x1_dev || pinned_host(a.x1)) && pinned_host(a.x2) && pinned_host(a.loss_host) && pinned_host(a.g1_host) &&
+                  pinned_host(a.g2_host)))
                 hit->plain = true;
             if (hit->exec == nullptr && !hit->plain) {
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
                 if (e == cudaSuccess) {
-                    e = enqueue_loss_step(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, ws, stream);
+                    e = enqueue_loss_step(a, ws, stream);
                     cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
                     if (e == cudaSuccess) e = e2;
                 }
@@ -391,17 +496,27 @@ int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host
             }
             if (hit->exec) {
                 cudaError_t e = cudaGraphLaunch(hit->exec, stream);
-                if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(graph launch)", e);
+                if (e != cudaSuccess) return finish("psd_chamfer_loss_step(graph launch)", e);
                 launched = true;
             }
         }
     }
     if (!launched) {
-        cudaError_t e = enqueue_loss_step(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, ws, stream);
-        if (e != cudaSuccess) return finish("psd_chamfer_loss_step_host(enqueue)", e);
+        cudaError_t e = enqueue_loss_step(a, ws, stream);
+        if (e != cudaSuccess) return finish("psd_chamfer_loss_step(enqueue)", e);
     }
+    api_lock.unlock();
     if (!sync) return 1;   // asynchronous: the caller synchronises `stream` before it reads loss_host / the gradients
-    return finish("psd_chamfer_loss_step_host(sync)", cudaStreamSynchronize(stream));
+    return finish("psd_chamfer_loss_step(sync)", cudaStreamSynchronize(stream));
+}
+
+int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
+                                  float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
+                                  int slot, int sync, void *stream_) {
+    StepArgs a;
+    a.x1 = xyz1_host; a.x2 = xyz2_host; a.b = b; a.n = n; a.m = m; a.loss_host = loss_host;
+    a.g1_host = gradxyz1_host; a.g2_host = gradxyz2_host;
+    return loss_step_common(a, gradxyz1_dev, gradxyz2_dev, slot, sync, stream_);
 }
 
 int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
@@ -409,6 +524,15 @@ int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, i
                                void *stream_) {
     return psd_chamfer_loss_step_host_ex(xyz1_host, xyz2_host, b, n, m, loss_host, gradxyz1_host, gradxyz2_host, gradxyz1_dev,
                                          gradxyz2_dev, 0, 1, stream_);
+}
+
+int psd_chamfer_loss_step_pred_dev(const float *xyz1_dev, int layout1, const float *xyz2_host, int b, int n, int m,
+                                   float *loss_host, float *gradxyz1_dev, int slot, int sync, void *stream_) {
+    if (layout1 != 0 && layout1 != 1) { psd_set_error_msg("psd_chamfer_loss_step_pred_dev: layout1 must be 0 ([B,N,3]) or 1 ([B,3,N])"); return -1; }
+    StepArgs a;
+    a.x1 = xyz1_dev; a.x1_dev = true; a.layout1 = layout1; a.x2 = xyz2_host; a.b = b; a.n = n; a.m = m; a.loss_host = loss_host;
+    a.g1_user = gradxyz1_dev;
+    return loss_step_common(a, nullptr, nullptr, slot, sync, stream_);
 }
 
 }  // extern "C"

@@ -41,9 +41,13 @@ class emdFunction(Function):
     def backward(ctx, graddist, gradidx):
         xyz1, xyz2, assignment = ctx.saved_tensors
         graddist = graddist.contiguous()
-        gradxyz1 = torch.zeros(xyz1.size(), device=xyz1.device)
-        gradxyz2 = torch.zeros(xyz2.size(), device=xyz1.device)
-        _lib.raise_on_cuda_error(emd.backward(xyz1, xyz2, gradxyz1, graddist, assignment), "emd.backward")
+        b, n, _ = xyz1.shape
+        gradxyz1 = torch.empty_like(xyz1)     # one term per address: stored by the kernel, no zero fill
+        with torch.cuda.device(xyz1.device):
+            rc = _lib.lib.psd_emd_backward_ex(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(gradxyz1), _lib.ptr(graddist),
+                                              _lib.ptr(assignment), b, n, 1, _lib.stream_of(xyz1))
+        _lib.raise_on_cuda_error(rc, "emd.backward")
+        gradxyz2 = torch.zeros_like(xyz2) if ctx.needs_input_grad[1] else None   # the reference returns zeros (emd_module.py:84-87)
         return gradxyz1, gradxyz2, None, None
 
 

@@ -27,14 +27,12 @@ def fscore(dist1, dist2, threshold=0.0001):
 
 
 def chamfer_fscore_fused(xyz1, xyz2, threshold=0.0001, layout=0):
-    """One launch: returns dict(dist1, dist2, idx1, idx2, sums[B,2], counts[B,2], fscore[B], precision_1[B],
+    """layout: bit mask of psd_chamfer_forward_ex (1: xyz1 is [B,3,N], 2: xyz2 is [B,3,M]).
+    One launch: returns dict(dist1, dist2, idx1, idx2, sums[B,2], counts[B,2], fscore[B], precision_1[B],
     precision_2[B], chamfer[B] = mean(dist1)+mean(dist2) per cloud)."""
-    if layout == 0:
-        b, n, _ = xyz1.shape
-        m = xyz2.shape[1]
-    else:
-        b, _, n = xyz1.shape
-        m = xyz2.shape[2]
+    b = xyz1.shape[0]
+    n = xyz1.shape[2] if layout & 1 else xyz1.shape[1]
+    m = xyz2.shape[2] if layout & 2 else xyz2.shape[1]
     dev = xyz1.device
     xyz1 = xyz1.contiguous()
     xyz2 = xyz2.contiguous()

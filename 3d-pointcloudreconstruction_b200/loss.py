@@ -3,11 +3,11 @@ import torch
 import torch.nn as nn
 
 try:
-    from .dist_chamfer_3D import chamfer_3DDist
+    from .dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffer_like
     from . import emd_module as emd_func
     from . import _lib
 except ImportError:
-    from dist_chamfer_3D import chamfer_3DDist
+    from dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffer_like
     import emd_module as emd_func
     import _lib
 
@@ -15,40 +15,92 @@ except ImportError:
 class _ChamferMeanLoss(torch.autograd.Function):
     """mean(dist1) + mean(dist2) (loss/loss.py:35-36) as ONE forward launch (+ a one-warp reduction) and ONE backward
     launch: the per-cloud sums come from the NN kernel's epilogue and the constant gradients 1/(B*N), 1/(B*M) are formed
-    inside the backward kernel (psd_chamfer_mean_loss_forward / _backward).  Results agree with the unfused path to fp32
-    summation-order noise (the sums are accumulated with float atomics)."""
+    inside the backward kernel (psd_chamfer_mean_loss_forward / _backward_ex), which stores the gradients without a zero
+    fill.  Clouds are read in place as [B,N,3] or as the transposed view of a [B,3,N] tensor (train.py:163).  Results agree
+    with the unfused path to fp32 summation-order noise (the sums are accumulated with float atomics)."""
 
     @staticmethod
     def forward(ctx, xyz1, xyz2):
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         dev = xyz1.device
+        xyz1, l1 = as_kernel_cloud(xyz1)
+        xyz2, l2 = as_kernel_cloud(xyz2)
+        layout = l1 | (l2 << 1)
         fbuf = torch.empty(b * (n + m), device=dev, dtype=torch.float32)
         ibuf = torch.empty(b * (n + m), device=dev, dtype=torch.int32)
         small = torch.zeros(2 * b + 1, device=dev, dtype=torch.float32)      # per-cloud sums [B,2] + the loss scalar
         idx1, idx2 = ibuf[: b * n], ibuf[b * n:]
         with torch.cuda.device(dev):
             rc = _lib.lib.psd_chamfer_mean_loss_forward(
-                _lib.ptr(xyz1), _lib.ptr(xyz2), b, n, m, 0, _lib.ptr(fbuf), _lib.ptr(fbuf[b * n:]), _lib.ptr(idx1),
+                _lib.ptr(xyz1), _lib.ptr(xyz2), b, n, m, layout, _lib.ptr(fbuf), _lib.ptr(fbuf[b * n:]), _lib.ptr(idx1),
                 _lib.ptr(idx2), _lib.ptr(small), _lib.ptr(small[2 * b:]), _lib.stream_of(xyz1))
-        _lib.raise_on_cuda_error(rc, "psd_chamfer_mean_loss_forward")
+        if rc != 1:
+            raise RuntimeError(f"psd_chamfer_mean_loss_forward failed (rc={rc}): {_lib.last_error()}")
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        ctx.layout = layout
         return small[2 * b]
 
     @staticmethod
     def backward(ctx, grad_loss):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        layout = ctx.layout
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         up = grad_loss.contiguous().to(torch.float32)
-        buf = torch.zeros(xyz1.numel() + xyz2.numel(), device=xyz1.device, dtype=torch.float32)
-        g1 = buf[: xyz1.numel()].view(xyz1.shape)
-        g2 = buf[xyz1.numel():].view(xyz2.shape)
+        g1 = grad_buffer_like(xyz1, layout & 1)
+        g2 = grad_buffer_like(xyz2, (layout >> 1) & 1)
         with torch.cuda.device(xyz1.device):
-            rc = _lib.lib.psd_chamfer_mean_loss_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(g1), _lib.ptr(g2), _lib.ptr(up),
-                                                         _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, _lib.stream_of(xyz1))
-        _lib.raise_on_cuda_error(rc, "psd_chamfer_mean_loss_backward")
+            rc = _lib.lib.psd_chamfer_mean_loss_backward_ex(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(g1), _lib.ptr(g2),
+                                                            _lib.ptr(up), _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, layout, 1,
+                                                            _lib.stream_of(xyz1))
+        if rc != 1:
+            raise RuntimeError(f"psd_chamfer_mean_loss_backward_ex failed (rc={rc}): {_lib.last_error()}")
         return g1, g2
+
+
+class _EmdMeanLoss(torch.autograd.Function):
+    """sqrt(dist).mean(1).mean() over emdModule's distances (loss/loss.py:23-25) with the square roots summed in the auction
+    kernel's CalcDist tail and the backward scale ((g/B)/n) / (2 sqrt(dist)) formed inside the gradient kernel
+    (psd_emd_mean_loss_forward / _backward): one forward launch (+ a one-warp reduction), one backward launch, no
+    intermediate tensors.  Like the reference's loss, a point that coincides with its assigned object gives an infinite
+    factor (NaN gradient); xyz2 receives zeros (emd_module.py:84-87)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, eps, iters):
+        b, n, _ = xyz1.shape
+        dev = xyz1.device
+        dist = torch.empty(b, n, device=dev, dtype=torch.float32)
+        assignment = torch.empty(b, n, device=dev, dtype=torch.int32)
+        small = torch.zeros(b + 1, device=dev, dtype=torch.float32)          # per-cloud sums [B] + the loss scalar
+        with torch.cuda.device(dev):
+            rc = _lib.lib.psd_emd_mean_loss_forward(_lib.ptr(xyz1), _lib.ptr(xyz2), b, n, _lib.ptr(dist), _lib.ptr(assignment),
+                                                    float(eps), int(iters), _lib.ptr(small), _lib.ptr(small[b:]),
+                                                    _lib.stream_of(xyz1))
+        if rc != 1:
+            raise RuntimeError(f"psd_emd_mean_loss_forward failed (rc={rc}): {_lib.last_error()}")
+        ctx.save_for_backward(xyz1, xyz2, dist, assignment)
+        return small[b]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        xyz1, xyz2, dist, assignment = ctx.saved_tensors
+        b, n, _ = xyz1.shape
+        up = grad_loss.contiguous().to(torch.float32)
+        g1 = torch.empty_like(xyz1)
+        with torch.cuda.device(xyz1.device):
+            rc = _lib.lib.psd_emd_mean_loss_backward(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(g1), _lib.ptr(dist),
+                                                     _lib.ptr(assignment), _lib.ptr(up), b, n, _lib.stream_of(xyz1))
+        if rc != 1:
+            raise RuntimeError(f"psd_emd_mean_loss_backward failed (rc={rc}): {_lib.last_error()}")
+        g2 = torch.zeros_like(xyz2) if ctx.needs_input_grad[1] else None
+        return g1, g2, None, None
+
+
+def _fusable(pred, gt):
+    return (pred.is_cuda and gt.is_cuda and pred.dtype == torch.float32 and gt.dtype == torch.float32 and pred.dim() == 3
+            and gt.dim() == 3 and pred.shape[2] == 3 and gt.shape[2] == 3 and pred.shape[0] == gt.shape[0]
+            and pred.device == gt.device and pred.numel() > 0 and gt.numel() > 0)
 
 
 class Loss(nn.Module):
@@ -61,15 +113,16 @@ class Loss(nn.Module):
     def get_emd_loss(self, pred, gt, radius=1.0, eps=0.05, iters=3000):
         """pred, gt: [B, N, 3].  sqrt(dist).mean(1).mean() with the training setting eps=0.05, iters=3000
         (loss/loss.py:23-25)."""
-        emd_1, _ = self._emd(pred, gt, eps=eps, iters=iters)
+        if (_fusable(pred, gt) and pred.shape[1] == gt.shape[1] and pred.shape[1] % 1024 == 0 and pred.shape[0] <= 512):
+            return _EmdMeanLoss.apply(pred.contiguous(), gt.contiguous(), eps, iters)
+        emd_1, _ = self._emd(pred, gt, eps=eps, iters=iters)       # the module's own asserts reject what the fused path cannot take
         return torch.sqrt(emd_1).mean(1).mean()
 
     def get_chamfer_loss(self, pred, gt):
-        """pred, gt: [B, N, 3].  mean(dist1) + mean(dist2) (loss/loss.py:35-36)."""
-        if (pred.is_cuda and gt.is_cuda and pred.dtype == torch.float32 and gt.dtype == torch.float32 and pred.dim() == 3
-                and gt.dim() == 3 and pred.shape[0] == gt.shape[0] and pred.numel() > 0 and gt.numel() > 0):
-            return _ChamferMeanLoss.apply(pred.contiguous(), gt.contiguous())   # fused epilogue + scalar-gradient backward
-        dist1, dist2, _, _ = self._cham(pred, gt)
+        """pred, gt: [B, N, 3] (or transposed views of [B, 3, N]).  mean(dist1) + mean(dist2) (loss/loss.py:35-36)."""
+        if _fusable(pred, gt):
+            return _ChamferMeanLoss.apply(pred, gt)   # fused epilogue + scalar-gradient backward, clouds read in place
+        dist1, dist2, _, _ = self._cham(pred, gt)     # asserts the last dimension like the reference
         return torch.mean(dist1) + torch.mean(dist2)
 
 

@@ -5,9 +5,9 @@ file defines the only exchange steps the path needs:
 * batch sharding (default): rank r owns clouds [start, start+count) end to end -- forward, backward, EMD.
   No data-path collective; one all_reduce of a tiny vector for the reported loss / F-score.
 * query sharding (large clouds, B < world): every rank holds the full clouds, runs the NN search for a 1/world
-  slice of the QUERY points of both directions (psd_chamfer_forward_ex q_begin/q_count), then
-  all_reduce(SUM) assembles dist/idx (disjoint slices, zeros elsewhere), the per-cloud sums and the F-score
-  counts.  Backward: each rank scatters the gradient terms of its own query slice, all_reduce(SUM) of grad_xyz.
+  slice of the QUERY points of both directions (psd_chamfer_forward_ex q_begin/q_count), then one all_reduce(SUM) each
+  for the per-cloud sums and the F-score counts and, when the full dist/idx are wanted on every rank, an
+  all_gather of the owned slices (or an all_reduce of zero-padded full tensors).  Backward: each rank scatters the gradient terms of its own query slice, all_reduce(SUM) of grad_xyz.
   EMD is never query-sharded (the auction state is per cloud and iterative).
 
 The local operator is injectable (`ops`) so that the partitioning / reduction logic can be tested on CPU
@@ -91,22 +91,47 @@ class _CudaOps:
 
 
 def chamfer_query_sharded(xyz1, xyz2, rank: int, world: int, threshold: float = 1e-4, group=None, ops=None,
-                          assemble: bool = True):
+                          assemble=True):
     """Query-sharded chamfer + F-score (BASELINE.json configs[4]).  Every rank passes the SAME full clouds.
 
     Returns a dict with the all-reduced per-cloud `sums` [B,2] and `counts` [B,2], the derived `chamfer` [B],
-    `fscore` [B], `precision_1/2` [B], the rank's query slice (`q_begin`, `q_count`) and, if `assemble`, the full
-    `dist1/dist2/idx1/idx2` (all_reduce over disjoint slices)."""
+    `fscore` [B], `precision_1/2` [B], the rank's query slices and, if `assemble`, the full `dist1/dist2/idx1/idx2` on
+    every rank: assemble=True / "all_gather" gathers the owned slices (one collective per tensor, 1/world of the bytes),
+    assemble="all_reduce" sums full-length tensors that are zero outside the owned slice.  Each direction's queries are
+    split on their own (n and m may differ)."""
     ops = ops or _CudaOps()
     b, n, _ = xyz1.shape
     m = xyz2.shape[1]
+    # one (begin, count) pair addresses both directions in psd_chamfer_forward_ex: split the longer cloud; the shorter
+    # direction is clipped to its own length by the kernel launcher
     q_begin, q_count = split_range(max(n, m), world, rank)
     out = ops.forward_slice(xyz1, xyz2, q_begin, q_count, threshold)
     sums = _all_reduce(out["sums"], group)
     counts = _all_reduce(out["counts"], group)
-    if assemble:
-        for k in ("dist1", "dist2", "idx1", "idx2"):
-            _all_reduce(out[k], group)
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if assemble and multi:
+        if assemble == "all_reduce":
+            for k in ("dist1", "dist2", "idx1", "idx2"):
+                _all_reduce(out[k], group)
+        else:
+            for k, total in (("dist1", n), ("dist2", m), ("idx1", n), ("idx2", m)):
+                # ranks split max(n, m); the shorter cloud's slices are the same ranges clipped to its length
+                per = -(-max(n, m) // world)
+                b_ = out[k].shape[0]
+                send = torch.zeros(b_, per, device=out[k].device, dtype=out[k].dtype)
+                lo, hi = min(q_begin, total), min(q_begin + q_count, total)
+                if hi > lo:
+                    send[:, : hi - lo] = out[k][:, lo:hi]
+                recv = torch.empty(world * b_, per, device=out[k].device, dtype=out[k].dtype)   # rank-major concatenation
+                dist.all_gather_into_tensor(recv, send, group=group)
+                recv = recv.view(world, b_, per)
+                full = torch.empty_like(out[k])
+                for r in range(world):
+                    rb, rc = split_range(max(n, m), world, r)
+                    lo_r, hi_r = min(rb, total), min(rb + rc, total)
+                    if hi_r > lo_r:
+                        full[:, lo_r:hi_r] = recv[r, :, : hi_r - lo_r]
+                out[k] = full
     p1 = counts[:, 0].float() / n
     p2 = counts[:, 1].float() / m
     f = 2 * p1 * p2 / (p1 + p2)

@@ -43,15 +43,16 @@ int psd_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int 
                         int *idx1, int *idx2, void *stream);
 
 /* Extended forward: the same NN search with fused epilogues and the generator's native layout.
- *   layout   : 0 = [B, N, 3] (reference layout), 1 = [B, 3, N] (the model output before
- *              fake.transpose(2,1), train.py:163 -- removes dist_chamfer_3D.py:79-80's .contiguous() copy).
+ *   layout   : bit mask.  bit 0 (1): xyz1 is [B, 3, N]; bit 1 (2): xyz2 is [B, 3, M]; a clear bit means the reference layout
+ *              [B, N, 3].  1 is the training step's call (train.py:163: the generator output fake[B,3,N] against the
+ *              ground truth points[B,N,3]) -- it removes dist_chamfer_3D.py:79-80's .contiguous() transpose copy.
  *   sums     : optional [B, 2] fp32, sums[b] += (sum_j dist1[b, j], sum_k dist2[b, k])   (loss/loss.py:36)
  *   fs_thr   : F-score threshold on the squared distances (loss/loss_.py:122, default 1e-4)
  *   fs_count : optional [B, 2] int32, fs_count[b] += (#{dist1[b,:] < thr}, #{dist2[b,:] < thr})  (loss_.py:132-133)
  * sums / fs_count are accumulated with atomics and must be zeroed by the caller.
  * q_begin/q_count select a slice of the QUERY points of both directions (query sharding across GPUs:
  * rank r passes its slice, targets stay whole); pass 0 and -1 for everything.  Outputs are still
- * indexed by the global query index. */
+ * indexed by the global query index.  Returns -1 for an invalid layout. */
 int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
                            float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, int q_begin,
                            int q_count, void *stream);
@@ -65,6 +66,14 @@ int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, i
 int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                          const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
                          int m, void *stream);
+
+/* The same gradient with the layouts of psd_chamfer_forward_ex (a gradient has the layout of its cloud) and, with
+ * overwrite != 0, WITHOUT the caller-zeroed contract: the kernel first stores every point's own term (each element of both
+ * gradients exactly once), passes a grid-wide barrier (cooperative launch) and then adds the scatter terms -- no memset
+ * before the launch and half the atomics.  overwrite == 0 accumulates like psd_chamfer_backward. */
+int psd_chamfer_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                            const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
+                            int m, int layout, int overwrite, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Earth mover's distance, auction approximation.
@@ -92,7 +101,9 @@ int psd_emd_forward_fresh(const float *xyz1, const float *xyz2, int b, int n, fl
                           int iters, void *stream);
 
 /* Test hook (not part of the reference surface): the same auction with the cluster size forced to
- * 1, 2, 4 or 8 CTAs per cloud, so that every decomposition can be parity-checked against the oracle. */
+ * 1, 2, 4 or 8 CTAs per cloud, so that every decomposition can be parity-checked against the oracle.  A NEGATIVE
+ * cluster_size runs the global-workspace form of the kernel (the one clouds of more than 8192 points take, whose state
+ * does not fit the shared memory of a cluster) with |cluster_size| CTAs per cloud. */
 int psd_emd_forward_cluster(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment,
                             float *price, int *assignment_inv, float eps, int iters, int cluster_size, void *stream);
 
@@ -101,6 +112,20 @@ int psd_emd_forward_cluster(const float *xyz1, const float *xyz2, int b, int n, 
  * gradxyz[b,j] += 2*graddist[b,j]*(xyz1[b,j] - xyz2[b,idx[b,j]]) (xyz1 only; emd_module.py:84-87). */
 int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
                      int b, int n, void *stream);
+/* overwrite != 0: gradxyz is stored, not accumulated (one term per address: no zero fill needed before the call). */
+int psd_emd_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx,
+                        int b, int n, int overwrite, void *stream);
+
+/* Fused training loss of the EMD term: Loss.get_emd_loss (loss/loss.py:18-28) = sqrt(dist).mean(1).mean() over emdModule's
+ * distances.  Forward: the auction kernel adds sum_j sqrt(dist[b, j]) to sums_zeroed[b] (zero-filled by the caller) in its
+ * CalcDist tail and a one-warp kernel reduces them to the scalar *loss (device); dist / assignment are still written.
+ * Backward: gradxyz1[b,j] = 2 g (xyz1[b,j] - xyz2[b,assignment[b,j]]) with g = ((*upstream / B) / n) / (2 sqrt(dist[b,j]))
+ * formed in the kernel (autograd's sequence, including the infinite factor at dist == 0; upstream NULL = 1.0); gradxyz1 is
+ * stored, not accumulated.  Same return convention as psd_emd_forward_fresh. */
+int psd_emd_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, float *dist, int *assignment, float eps,
+                              int iters, float *sums_zeroed, float *loss, void *stream);
+int psd_emd_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, const float *dist, const int *assignment,
+                               const float *upstream, int b, int n, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused training loss of the hot path's caller: Loss.get_chamfer_loss (loss/loss.py:30-37) =
@@ -109,11 +134,15 @@ int psd_emd_backward(const float *xyz1, const float *xyz2, float *gradxyz, const
  * dist/idx are still written.  Backward: what autograd would hand to psd_chamfer_backward for this loss, graddist1 =
  * *upstream/(B*N), graddist2 = *upstream/(B*M), is formed inside the kernel from the device scalar `upstream`
  * (NULL = 1.0), so no gradient tensors are materialised; gradxyz1/gradxyz2 must be zero-filled by the caller.
- * Same return convention as above. */
+ * The _ex form takes the layout mask of psd_chamfer_forward_ex and, with overwrite != 0, needs no zero fill
+ * (see psd_chamfer_backward_ex).  Same return convention as above. */
 int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
                                   float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, void *stream);
 int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                    const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream);
+int psd_chamfer_mean_loss_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
+                                      const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, int layout,
+                                      int overwrite, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * psd_proj_min_dist  =  the min-distance branch of get_loss_proj, loss/proj_loss.py:21-40 (with grid_dist, :46-54).
@@ -165,6 +194,12 @@ int psd_farthest_point_sample(const float *xyz, int b, int n, int npoint, int st
  * is the last ulp of expf.  Returns 1 ok / 0 CUDA error / -1 argument error.
  * ------------------------------------------------------------------------------------------- */
 int psd_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out, void *stream);
+/* Its backward (the reference's cont_proj is differentiable torch code): grad_pcl [B, N, 3] = d loss / d pcl for
+ * grad_out [B, grid_h, grid_w] = d loss / d out; the z component is zero.  grad_pcl is stored, not accumulated.  The gradient
+ * image of a sample is staged in shared memory: grid_h * (grid_w + 1) + 8 (grid_h + grid_w) floats <= 200 KB (about 220 x 220),
+ * else -1. */
+int psd_cont_proj_backward(const float *pcl, const float *grad_out, int b, int n, int grid_h, int grid_w, float sigma_sq,
+                           float *grad_pcl, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (end-to-end path: pinned or pageable HOST pointers, the library
@@ -188,6 +223,12 @@ int psd_chamfer_loss_step_host(const float *xyz1_host, const float *xyz2_host, i
 int psd_chamfer_loss_step_host_ex(const float *xyz1_host, const float *xyz2_host, int b, int n, int m, float *loss_host,
                                   float *gradxyz1_host, float *gradxyz2_host, float **gradxyz1_dev, float **gradxyz2_dev,
                                   int slot, int sync, void *stream);
+/* The training step as the reference's loop has it (train.py:160-163): the PREDICTION is already on the device (the
+ * generator's output, layout1 = 1 for its native [B,3,N], 0 for [B,N,3]) and only the ground truth comes from the host.
+ * H2D of xyz2, forward, fused mean loss, backward; d loss / d xyz1 is stored to gradxyz1_dev (device, the layout of xyz1; NULL =
+ * kept in the workspace), the loss is copied to *loss_host.  slot / sync / stream as above. */
+int psd_chamfer_loss_step_pred_dev(const float *xyz1_dev, int layout1, const float *xyz2_host, int b, int n, int m,
+                                   float *loss_host, float *gradxyz1_dev, int slot, int sync, void *stream);
 /* Repeated calls of the host step with the same pinned buffers, shape, slot and a non-default stream are replayed from a
  * cached CUDA graph (one cudaGraphLaunch instead of nine API calls per step) from the second sighting on; pageable
  * buffers and the default stream always take the plain path.  enable: 0 / 1 sets it, anything else only queries;
@@ -207,8 +248,8 @@ int psd_fp32_fma_peak(float ms_target, float *tflops, void *stream);
 int psd_chamfer_stats(long long *out_host2, int reset);
 
 /* Test/measurement hook: choose the chamfer NN forward kernel.  0 = automatic (default: the tensor-core kernel when
- * both clouds have <= 2048 points, else the FFMA kernels), 1 = shared-block FFMA kernel, 2 = grouped FFMA kernel,
- * 3 = tensor-core (tcgen05) kernel.  All produce identical results.  Returns the previous setting. */
+ * the launch has at least two 128-query units per SM, else the FFMA kernel), 1 = FFMA kernel, 3 = tensor-core (tcgen05)
+ * kernel; any other value only queries.  Both produce identical results.  Returns the previous setting. */
 int psd_chamfer_nn_variant(int variant);
 
 /* Test / profiling switch of the auction kernel's solo mode (once a cloud is down to <= 32 unassigned points, one CTA of its

@@ -8,11 +8,10 @@ from conftest import make_clouds
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["auto", "shared_block", "grouped", "tensor_core"], autouse=True)
+@pytest.fixture(params=[0, 1, 3], ids=["auto", "ffma", "tensor_core"], autouse=True)
 def nn_variant(request, pkg):
     """Every test of this file runs against every NN forward kernel (psd_chamfer_nn_variant): the automatic choice, the
-    two FFMA kernels (shared-block, grouped) and the tcgen05 tensor-core kernel (clouds of <= 2048 points; larger
-    shapes fall through to the FFMA kernels)."""
+    FFMA kernel and the tcgen05 tensor-core kernel (clouds of more than 2048 points: its multi-tile mode)."""
     old = pkg._lib.lib.psd_chamfer_nn_variant(request.param)
     yield request.param
     pkg._lib.lib.psd_chamfer_nn_variant(old)
@@ -279,7 +278,7 @@ def test_soa_layout_matches_aos(pkg, oracle, cuda):
     """[B,3,N] input (the generator's native layout, train.py:163) gives the same bits without a transpose copy."""
     x, y = make_clouds("uniform", 3, 777, 1029, seed=41)
     tx, ty = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
-    out = pkg.chamfer_fscore_fused(tx.transpose(1, 2).contiguous(), ty.transpose(1, 2).contiguous(), layout=1)
+    out = pkg.chamfer_fscore_fused(tx.transpose(1, 2).contiguous(), ty.transpose(1, 2).contiguous(), layout=3)
     want = oracle.chamfer_forward(x, y, nthreads=8)
     assert_bit_equal([out[k].cpu().numpy() for k in ("dist1", "dist2", "idx1", "idx2")], want, "soa")
 

@@ -64,6 +64,13 @@ def _worker(rank, world, port, ret):
         out = sh.chamfer_query_sharded(tx, ty, rank, world, threshold=1e-3, ops=OracleOps())
         d1, d2, i1, i2 = O.chamfer_forward(x, y)
         ok["assemble"] = all(np.array_equal(out[k].numpy(), w) for k, w in (("dist1", d1), ("dist2", d2), ("idx1", i1), ("idx2", i2)))
+        out_ar = sh.chamfer_query_sharded(tx, ty, rank, world, threshold=1e-3, ops=OracleOps(), assemble="all_reduce")
+        ok["assemble_all_reduce"] = all(np.array_equal(out_ar[k].numpy(), w) for k, w in (("dist1", d1), ("dist2", d2), ("idx1", i1), ("idx2", i2)))
+        # very asymmetric clouds: the shorter direction's queries all belong to rank 0 (rank 1 owns an empty slice of it)
+        xa, ya = make_clouds("uniform", 2, 700, 40, seed=6)
+        oa = sh.chamfer_query_sharded(torch.from_numpy(xa), torch.from_numpy(ya), rank, world, ops=OracleOps())
+        wa = O.chamfer_forward(xa, ya)
+        ok["asymmetric"] = all(np.array_equal(oa[k].numpy(), w) for k, w in zip(("dist1", "dist2", "idx1", "idx2"), wa))
         c1, c2 = O.fscore_counts(d1, d2, 1e-3)
         ok["counts"] = np.array_equal(out["counts"].numpy(), np.stack([c1, c2], 1))
         ok["sums"] = np.allclose(out["sums"].numpy(), np.stack([d1.sum(1), d2.sum(1)], 1), rtol=1e-5)

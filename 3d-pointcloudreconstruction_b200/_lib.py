@@ -49,6 +49,7 @@ _SIGNATURES = {
     "psd_emd_solo_mode": [_ci],
     "psd_emd_grid_mode": [_ci],
     "psd_chamfer_tc_ctas": [_ci],
+    "psd_chamfer_grad_mode": [_ci, _ci],
     "psd_proj_min_dist": [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],
     "psd_icp_batch": [_vp, _vp, _ci, _ci, _ci, _vp, _ci, ctypes.c_double, _vp, _vp, _vp, _vp],
     "psd_nn_f64": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],

@@ -32,5 +32,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+PYBIND_DIR = os.path.join(HERE, "pybind")
+
+
+def build_pybind(verbose: bool = False) -> str:
+    """Compile pybind/psd_pybind.cpp into the reference's two native module names, `chamfer_3D` and `emd`, linked against
+    libpsd_b200.so (rpath = this directory).  The modules land in pybind/_build/ (git-ignored, shipped to the GPU box); put
+    that directory on sys.path and the reference's unmodified dist_chamfer_3D.py / emd_module.py import them."""
+    build()
+    from torch.utils.cpp_extension import load
+
+    out = os.path.join(PYBIND_DIR, "_build")
+    src = os.path.join(PYBIND_DIR, "psd_pybind.cpp")
+    for name, macro in (("chamfer_3D", "-DPSD_BIND_CHAMFER"), ("emd", "-DPSD_BIND_EMD")):
+        bdir = os.path.join(out, "obj_" + name)
+        os.makedirs(bdir, exist_ok=True)
+        so = os.path.join(out, name + ".so")
+        if os.path.exists(so) and os.path.getmtime(so) >= max(os.path.getmtime(src), os.path.getmtime(OUT)):
+            continue
+        load(name=name, sources=[src], build_directory=bdir, is_python_module=False, verbose=verbose,
+             extra_cflags=["-O2", macro], extra_include_paths=[os.path.join(HERE, "..", "include")],
+             extra_ldflags=["-L" + HERE, "-lpsd_b200", "-Wl,-rpath," + HERE], with_cuda=True)
+        import shutil
+        shutil.copy2(os.path.join(bdir, name + ".so"), so)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    if "--pybind" in sys.argv:
+        print(build_pybind(verbose="-v" in sys.argv))

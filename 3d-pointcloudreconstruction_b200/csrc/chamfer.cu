@@ -543,8 +543,12 @@ __device__ __forceinline__ void grad_scatter(const GradParams &p, bool active, c
     }
 }
 
-template <bool OVERWRITE>
+// MODE 0: accumulate (own-point and scatter terms as atomics, caller-zeroed buffers)
+// MODE 1: overwrite, ONE cooperative launch: store own-point terms, grid barrier, scatter atomics
+// MODE 2 / 3: overwrite as TWO plain launches (2 = store own-point terms, 3 = scatter atomics): stream order is the barrier
+template <int MODE>
 __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
+    constexpr bool OVERWRITE = MODE != 0;
     const long long nthreads = (long long)gridDim.x * blockDim.x;   // a multiple of 32
     const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
     GradTerm t0;
     t0.d2 = false; t0.own = 0; t0.tgt = -1 - (long long)lane; t0.v[0] = t0.v[1] = t0.v[2] = 0.f;
     if (active0) t0 = grad_term(p, gid0);
-    if (OVERWRITE) {
+    if (MODE == 1 || MODE == 2) {
         auto store_own = [&](const GradTerm &t) {
             float *o = (t.d2 ? p.g2 : p.g1) + t.own;
             const long long csa = t.d2 ? p.cs2 : p.cs1;
@@ -561,6 +565,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
         };
         if (active0) store_own(t0);
         for (long long gid = gid0 + nthreads; gid < p.total; gid += nthreads) store_own(grad_term(p, gid));
+        if (MODE == 2) return;
         __threadfence();
         cooperative_groups::this_grid().sync();
     }
@@ -596,6 +601,14 @@ static std::atomic<int> g_nn_variant{0};   // 0 = auto, 1 = FFMA kernel (this fi
 static std::atomic<float *> g_tc_dbg{nullptr};   // one-shot debug dump target of the tensor-core kernel (psd_debug_tc_filter)
 static std::atomic<int> g_tc_dbg_ld{0};
 static std::atomic<long long *> g_tc_prof{nullptr};
+static std::atomic<int> g_grad_split{0};      // overwrite backward: 0 = one cooperative launch, 1 = two plain launches
+static std::atomic<int> g_grad_max_ctas{0};   // upper bound on the cooperative backward's grid (0 = whatever is co-resident)
+int psd_set_grad_mode(int split, int max_ctas) {
+    const int old = g_grad_split.load() | (g_grad_max_ctas.load() << 1);
+    if (split == 0 || split == 1) g_grad_split.store(split);
+    if (max_ctas >= 0) g_grad_max_ctas.store(max_ctas);
+    return old;
+}
 
 bool psd_nn_tc_supported(const NNParams &p);                                               // chamfer_nn_tc.cu
 cudaError_t psd_launch_nn_tc(const NNParams &p, DeviceState *ds, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b);
@@ -707,9 +720,14 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
     layout_strides(layout, 1, n, p.ps1, p.cs1);
     layout_strides(layout, 2, m, p.ps2, p.cs2);
     const long long blocks = (p.total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (!overwrite) {
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        chamfer_grad_kernel<false><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+        chamfer_grad_kernel<0><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    if (g_grad_split.load()) {   // two plain launches: stream order is the barrier between the stores and the atomics
+        chamfer_grad_kernel<2><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+        chamfer_grad_kernel<3><<<(unsigned int)blocks, 256, 0, stream>>>(p);
         return cudaGetLastError();
     }
     cudaError_t derr = cudaSuccess;
@@ -720,16 +738,18 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
         std::lock_guard<std::mutex> lock(state_mutex());
         if (ds->grad_ctas_per_sm == 0) {
             int occ = 0;
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chamfer_grad_kernel<true>, 256, 0);
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chamfer_grad_kernel<1>, 256, 0);
             if (e != cudaSuccess) return e;
             ds->grad_ctas_per_sm = occ > 0 ? occ : 1;
         }
         per_sm = ds->grad_ctas_per_sm;
     }
-    const long long resident = (long long)per_sm * ds->num_sms;   // a cooperative launch must be co-resident
+    long long resident = (long long)per_sm * ds->num_sms;   // a cooperative launch must be co-resident
+    const int cap = g_grad_max_ctas.load();
+    if (cap > 0 && resident > cap) resident = cap;
     const unsigned int grid = (unsigned int)(blocks < resident ? blocks : resident);
     void *args[] = {(void *)&p};
-    return cudaLaunchCooperativeKernel((const void *)chamfer_grad_kernel<true>, dim3(grid), dim3(256), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void *)chamfer_grad_kernel<1>, dim3(grid), dim3(256), args, 0, stream);
 }
 
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {

@@ -26,6 +26,7 @@ int psd_icp_max_points();
 int psd_set_emd_solo(int enable);
 int psd_set_emd_grid(int enable);
 int psd_set_tc_max_ctas(int n);
+int psd_set_grad_mode(int split, int max_ctas);
 cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
                                  cudaStream_t stream);
 cudaError_t psd_launch_cont_proj_backward(const float *pcl, const float *gout, int b, int n, int grid_h, int grid_w,
@@ -282,6 +283,8 @@ int psd_emd_solo_mode(int enable) { return psd_set_emd_solo(enable); }
 int psd_emd_grid_mode(int enable) { return psd_set_emd_grid(enable); }
 
 int psd_chamfer_tc_ctas(int max_ctas) { return psd_set_tc_max_ctas(max_ctas); }
+
+int psd_chamfer_grad_mode(int split, int max_ctas) { return psd_set_grad_mode(split, max_ctas); }
 
 int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
 

@@ -181,6 +181,27 @@ class ChamferLossPipeline:
         _lib.raise_on_cuda_error(rc, "psd_chamfer_loss_step_host_ex")
         self.pending.append(slot)
 
+    def submit_pred_dev(self, pred_dev, layout1, gt_host, grad_pred_dev=None):
+        """The training loop's real shape (train.py:160-163): the prediction is a DEVICE tensor (layout1 = 1: the generator's
+        contiguous [B,3,N] output, 0: [B,N,3]) that the caller's stream has finished writing, only the ground truth is copied from the host;
+        d loss / d pred is stored into grad_pred_dev (same layout) when given (psd_chamfer_loss_step_pred_dev, sync = 0)."""
+        import ctypes
+        assert len(self.pending) < self.depth, "pipeline full: call result() first"
+        slot = self.n % self.depth
+        self.n += 1
+        b = pred_dev.shape[0]
+        n = pred_dev.shape[2] if layout1 else pred_dev.shape[1]
+        m = gt_host.shape[1]
+        with torch.cuda.device(self.dev):
+            rc = _lib.lib.psd_chamfer_loss_step_pred_dev(
+                ctypes.c_void_p(pred_dev.data_ptr()), int(layout1), ctypes.c_void_p(gt_host.data_ptr()), b, n, m,
+                ctypes.c_void_p(self.loss.data_ptr() + 4 * slot),
+                ctypes.c_void_p(grad_pred_dev.data_ptr()) if grad_pred_dev is not None else None, slot, 0,
+                ctypes.c_void_p(self.streams[slot].cuda_stream))
+        if rc != 1:
+            raise RuntimeError(f"psd_chamfer_loss_step_pred_dev failed (rc={rc}): {_lib.last_error()}")
+        self.pending.append(slot)
+
     def result(self):
         slot = self.pending.popleft()
         self.streams[slot].synchronize()

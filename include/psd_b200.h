@@ -265,6 +265,13 @@ int psd_emd_grid_mode(int enable);
  * the other stream fills the remaining SMs.  Returns the previous value.  Results are identical. */
 int psd_chamfer_tc_ctas(int max_ctas);
 
+/* Form of the overwrite backward (psd_chamfer_backward_ex with overwrite != 0).  split: 0 = one cooperative launch with a
+ * grid-wide barrier between the stores and the scatter atomics (default), 1 = two plain launches (stream order is the
+ * barrier); max_ctas: upper bound on the cooperative grid (0 = as many 256-thread CTAs as are co-resident), for callers
+ * that keep several launches in flight and do not want a backward to wait for most of the GPU.  Negative values only query.
+ * Returns split | max_ctas << 1 as they were.  Results are identical in every form. */
+int psd_chamfer_grad_mode(int split, int max_ctas);
+
 /* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
  * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a
  * unit is a block of 128 queries in launch order (direction 1 blocks first).  dump_ld >= n and m rounded up to 128. */

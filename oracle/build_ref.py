@@ -1,8 +1,10 @@
 """Compile the UNMODIFIED reference CUDA extensions into oracle/_ref/ (test infrastructure only).
 
-The sources are compiled where they lie under /root/reference (nothing is copied into this repo):
+The sources are compiled where they lie under /root/reference (nothing enters this repo's history):
     metric/chamfer3D/{chamfer_cuda.cpp,chamfer3D.cu}  -> oracle/_ref/ref_chamfer_3D.so
     metric/emd/{emd.cpp,emd_cuda.cu}                  -> oracle/_ref/ref_emd.so
+    metric/chamfer3D/dist_chamfer_3D.py, metric/emd/emd_module.py, loss/loss_.py -> oracle/_ref/py/ (verbatim copies, so that
+    the GPU box -- which has no /root/reference -- can run the reference's own Python on top of either native module)
 Flags are the ones torch's BuildExtension would pass for the reference's own setup.py (no
 --use_fast_math: -fmad=true, IEEE sqrt/div, no FTZ), with the arch pinned to sm_100a.  The module
 names carry a ref_ prefix (TORCH_EXTENSION_NAME) so they can be imported next to this repo's drop-in
@@ -44,6 +46,14 @@ def build(verbose: bool = False) -> bool:
             verbose=verbose,
         )
         print(f"[build_ref] built {name} in {bdir}")
+    # the reference's own Python wrappers / CPU chamfer, byte for byte, next to its compiled extensions (git-ignored like
+    # them): tests run them UNMODIFIED on top of this repo's pybind modules, bench.py --impl reference times loss_.py
+    import shutil
+    pdir = os.path.join(OUT, "py")
+    os.makedirs(pdir, exist_ok=True)
+    for rel in ("metric/chamfer3D/dist_chamfer_3D.py", "metric/emd/emd_module.py", "loss/loss_.py"):
+        shutil.copy2(os.path.join(REF, rel), os.path.join(pdir, os.path.basename(rel)))
+    print(f"[build_ref] copied the reference's Python wrappers to {pdir}")
     return True
 
 

@@ -13,8 +13,13 @@ PKG_NAME = "pointcloudreconstruction_b200"
 
 
 def load():
+    """Import the package; (re)build libpsd_b200.so first when it is missing or older than its sources (needs nvcc; a box
+    without nvcc keeps the shipped library, and a missing library still fails loudly in _lib.py)."""
     if PKG_NAME in sys.modules:
         return sys.modules[PKG_NAME]
+    import shutil
+    if shutil.which(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) and not os.environ.get("PSD_B200_LIB"):
+        build(force=False)
     spec = importlib.util.spec_from_file_location(
         PKG_NAME, os.path.join(PKG_DIR, "__init__.py"), submodule_search_locations=[PKG_DIR])
     mod = importlib.util.module_from_spec(spec)
@@ -32,6 +37,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.build(force=force, verbose=verbose)
+
+
+def build_pybind(verbose: bool = False) -> str:
+    """Compile the pybind modules `chamfer_3D` / `emd` over the C ABI (3d-pointcloudreconstruction_b200/pybind)."""
+    spec = importlib.util.spec_from_file_location("_psd_b200_build", os.path.join(PKG_DIR, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build_pybind(verbose=verbose)
 
 
 def add_to_sys_path():

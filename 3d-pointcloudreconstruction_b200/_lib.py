@@ -26,6 +26,7 @@ _cf = ctypes.c_float
 _SIGNATURES = {
     "psd_chamfer_forward": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp],
     "psd_chamfer_forward_ex": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _cf, _vp, _ci, _ci, _vp],
+    "psd_chamfer_forward_zero": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _cf, _vp, _vp, ctypes.c_longlong, _vp],
     "psd_chamfer_backward": [_vp] * 8 + [_ci, _ci, _ci, _vp],
     "psd_chamfer_backward_ex": [_vp] * 8 + [_ci, _ci, _ci, _ci, _ci, _vp],
     "psd_emd_forward": [_vp, _vp, _ci, _ci, _ci] + [_vp] * 12 + [_cf, _ci, _vp],
@@ -40,6 +41,7 @@ _SIGNATURES = {
     "psd_chamfer_stats": [ctypes.POINTER(ctypes.c_longlong), _ci],
     "psd_chamfer_nn_variant": [_ci],
     "psd_chamfer_mean_loss_forward": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "psd_chamfer_mean_loss_forward_zero": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_longlong, _vp],
     "psd_chamfer_mean_loss_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _vp],
     "psd_chamfer_mean_loss_backward_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _vp],
     "psd_chamfer_loss_step_host": [_vp, _vp, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -49,7 +51,6 @@ _SIGNATURES = {
     "psd_emd_solo_mode": [_ci],
     "psd_emd_grid_mode": [_ci],
     "psd_chamfer_tc_ctas": [_ci],
-    "psd_chamfer_grad_mode": [_ci, _ci],
     "psd_proj_min_dist": [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],
     "psd_icp_batch": [_vp, _vp, _ci, _ci, _ci, _vp, _ci, ctypes.c_double, _vp, _vp, _vp, _vp],
     "psd_nn_f64": [_vp, _vp, _ci, _ci, _ci, _ci, _vp, _vp, _vp],

@@ -20,8 +20,6 @@
 //     order with strict '<'.  Otherwise (near-ties, duplicated points, non-finite input) the query takes
 //     an exact full scan that also reproduces the reference's NaN/512-tile semantics.
 //   => dist/idx are always produced by the exact formula; the filter only decides where to look.
-#include <cooperative_groups.h>
-
 #include "chamfer_nn.cuh"
 #include "psd_device.h"
 
@@ -65,6 +63,7 @@ __global__ void __launch_bounds__(kThreads, 1) chamfer_nn_kernel(const NNParams 
     const int G = gridDim.x;
     const int blk_begin = (int)(((long long)blockIdx.x * p.total_blocks) / G);
     const int blk_end = (int)(((long long)(blockIdx.x + 1) * p.total_blocks) / G);
+    zero_fill(p);
 
     float cx = 0.f, cy = 0.f, cz = 0.f;   // filter-frame centre of group c_group
     int c_group = -1;
@@ -458,9 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) chamfer_nn_kernel(const NNParams 
 // Two forms:
 //   OVERWRITE = false  the reference's contract (chamfer3D.cu:177-178): accumulate into caller-zeroed buffers, every
 //                      term an atomic.
-//   OVERWRITE = true   the gradients need no initialisation: phase 1 STORES the own-point terms (every element of
-//                      both gradients is written exactly once), a grid-wide barrier (cooperative launch), then phase 2
-//                      adds the scatter terms.  No memset before the launch and half the atomics.
+//   OVERWRITE = true   the gradients need no initialisation: a first launch STORES the own-point terms (every element of
+//                      both gradients is written exactly once), a second launch adds the scatter terms.
 // Clouds and their gradients are addressed through (point, component) strides, so the generator's native
 // [B,3,N] layout (train.py:160-163) needs no transpose copy in either direction.
 // ------------------------------------------------------------------------------------------------
@@ -544,20 +542,21 @@ __device__ __forceinline__ void grad_scatter(const GradParams &p, bool active, c
 }
 
 // MODE 0: accumulate (own-point and scatter terms as atomics, caller-zeroed buffers)
-// MODE 1: overwrite, ONE cooperative launch: store own-point terms, grid barrier, scatter atomics
-// MODE 2 / 3: overwrite as TWO plain launches (2 = store own-point terms, 3 = scatter atomics): stream order is the barrier
+// MODE 2 / 3: overwrite as TWO plain launches (2 = store own-point terms, 3 = scatter atomics): stream order is the barrier.
+// (A single cooperative launch with a grid-wide barrier in between was measured SLOWER on B200: 11.2 us against 9.4 us for the
+// two launches and 8.1 us for zero fill + MODE 0 at config 2, tools/grad_forms.py -- and it would have to wait for most of
+// the GPU when several steps are in flight.  The fast path is MODE 0 on buffers that the forward kernel zero-filled.)
 template <int MODE>
 __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
     constexpr bool OVERWRITE = MODE != 0;
     const long long nthreads = (long long)gridDim.x * blockDim.x;   // a multiple of 32
     const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    // the thread's first term stays in registers across the barrier (most launches have one term per thread)
     const bool active0 = gid0 < p.total;
     GradTerm t0;
     t0.d2 = false; t0.own = 0; t0.tgt = -1 - (long long)lane; t0.v[0] = t0.v[1] = t0.v[2] = 0.f;
     if (active0) t0 = grad_term(p, gid0);
-    if (MODE == 1 || MODE == 2) {
+    if (MODE == 2) {
         auto store_own = [&](const GradTerm &t) {
             float *o = (t.d2 ? p.g2 : p.g1) + t.own;
             const long long csa = t.d2 ? p.cs2 : p.cs1;
@@ -565,9 +564,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
         };
         if (active0) store_own(t0);
         for (long long gid = gid0 + nthreads; gid < p.total; gid += nthreads) store_own(grad_term(p, gid));
-        if (MODE == 2) return;
-        __threadfence();
-        cooperative_groups::this_grid().sync();
+        return;
     }
     grad_scatter<OVERWRITE>(p, active0, t0, lane);
     for (long long base = gid0 - lane + nthreads; base < p.total; base += nthreads) {   // warp-uniform trip count
@@ -601,14 +598,6 @@ static std::atomic<int> g_nn_variant{0};   // 0 = auto, 1 = FFMA kernel (this fi
 static std::atomic<float *> g_tc_dbg{nullptr};   // one-shot debug dump target of the tensor-core kernel (psd_debug_tc_filter)
 static std::atomic<int> g_tc_dbg_ld{0};
 static std::atomic<long long *> g_tc_prof{nullptr};
-static std::atomic<int> g_grad_split{0};      // overwrite backward: 0 = one cooperative launch, 1 = two plain launches
-static std::atomic<int> g_grad_max_ctas{0};   // upper bound on the cooperative backward's grid (0 = whatever is co-resident)
-int psd_set_grad_mode(int split, int max_ctas) {
-    const int old = g_grad_split.load() | (g_grad_max_ctas.load() << 1);
-    if (split == 0 || split == 1) g_grad_split.store(split);
-    if (max_ctas >= 0) g_grad_max_ctas.store(max_ctas);
-    return old;
-}
 
 bool psd_nn_tc_supported(const NNParams &p);                                               // chamfer_nn_tc.cu
 cudaError_t psd_launch_nn_tc(const NNParams &p, DeviceState *ds, cudaStream_t stream, float *dbg, int dbg_ld, long long *prof, int b);
@@ -628,8 +617,11 @@ static inline void layout_strides(int layout, int bit, int npts, long long &ps, 
 
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
                                        float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
-                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream) {
-    if (b <= 0 || n <= 0 || m <= 0) return cudaSuccess;
+                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream, float *zero_buf,
+                                       long long zero_floats) {
+    if (zero_floats <= 0) zero_buf = nullptr;
+    auto only_zero = [&]() { return zero_buf ? cudaMemsetAsync(zero_buf, 0, sizeof(float) * (size_t)zero_floats, stream) : cudaSuccess; };
+    if (b <= 0 || n <= 0 || m <= 0) return only_zero();
     cudaError_t derr = cudaSuccess;
     DeviceState *ds = device_state(&derr);
     if (ds == nullptr) return derr;
@@ -652,8 +644,9 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     fill(p.dir[0], xyz1, n, 1, xyz2, m, 2, dist1, idx1, 0);
     fill(p.dir[1], xyz2, m, 2, xyz1, n, 1, dist2, idx2, 1);
     const long long blocks = (long long)b * (p.dir[0].qblocks + p.dir[1].qblocks);
-    if (blocks == 0) return cudaSuccess;
+    if (blocks == 0) return only_zero();
     if (blocks > 0x3fffffffLL) return cudaErrorInvalidConfiguration;
+    p.zero_buf = zero_buf; p.zero_floats = zero_floats;
     p.blocks_dir0 = b * p.dir[0].qblocks;
     p.total_blocks = (int)blocks;
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
@@ -725,31 +718,10 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
         chamfer_grad_kernel<0><<<(unsigned int)blocks, 256, 0, stream>>>(p);
         return cudaGetLastError();
     }
-    if (g_grad_split.load()) {   // two plain launches: stream order is the barrier between the stores and the atomics
-        chamfer_grad_kernel<2><<<(unsigned int)blocks, 256, 0, stream>>>(p);
-        chamfer_grad_kernel<3><<<(unsigned int)blocks, 256, 0, stream>>>(p);
-        return cudaGetLastError();
-    }
-    cudaError_t derr = cudaSuccess;
-    DeviceState *ds = device_state(&derr);
-    if (ds == nullptr) return derr;
-    int per_sm;
-    {
-        std::lock_guard<std::mutex> lock(state_mutex());
-        if (ds->grad_ctas_per_sm == 0) {
-            int occ = 0;
-            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chamfer_grad_kernel<1>, 256, 0);
-            if (e != cudaSuccess) return e;
-            ds->grad_ctas_per_sm = occ > 0 ? occ : 1;
-        }
-        per_sm = ds->grad_ctas_per_sm;
-    }
-    long long resident = (long long)per_sm * ds->num_sms;   // a cooperative launch must be co-resident
-    const int cap = g_grad_max_ctas.load();
-    if (cap > 0 && resident > cap) resident = cap;
-    const unsigned int grid = (unsigned int)(blocks < resident ? blocks : resident);
-    void *args[] = {(void *)&p};
-    return cudaLaunchCooperativeKernel((const void *)chamfer_grad_kernel<1>, dim3(grid), dim3(256), args, 0, stream);
+    // two plain launches: stream order is the barrier between the stores and the atomics
+    chamfer_grad_kernel<2><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+    chamfer_grad_kernel<3><<<(unsigned int)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t psd_read_chamfer_stats(unsigned long long *fallback, int reset) {

@@ -1,5 +1,5 @@
 // chamfer_nn.cuh -- launch description shared by the two Chamfer NN forward kernels
-// (chamfer.cu: shared-block kernel for small launches; chamfer_nn_grouped.cu: grouped kernel).
+// (chamfer.cu: FFMA kernel for small launches; chamfer_nn_tc.cu: tensor-core kernel).
 #pragma once
 #include "psd_common.cuh"
 
@@ -39,7 +39,23 @@ struct NNParams {
     float *sums;        // optional [B,2]
     int *fs_count;      // optional [B,2]
     float fs_thr;
+    // optional: a buffer the launch also zero-fills (the gradient buffers of the backward that follows on the stream), so
+    // that a training step needs no separate memset
+    float *zero_buf;
+    long long zero_floats;
 };
+
+// grid-wide zero fill of p.zero_buf, a few stores per thread, issued before anything else in the forward kernels
+__device__ __forceinline__ void zero_fill(const NNParams &p) {
+    if (p.zero_buf == nullptr) return;
+    const long long nth = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (((reinterpret_cast<unsigned long long>(p.zero_buf) & 15ull) == 0ull) && (p.zero_floats & 3) == 0) {
+        float4 *z = reinterpret_cast<float4 *>(p.zero_buf);
+        for (long long i = t0; i < (p.zero_floats >> 2); i += nth) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (long long i = t0; i < p.zero_floats; i += nth) p.zero_buf[i] = 0.f;
+    }
+}
 
 // exact squared distance of query (x1,y1,z1) to target k of a cloud with generic strides
 __device__ __forceinline__ float exact_d(const float *__restrict__ tb, long long tps, long long tcs, int k, float x1,

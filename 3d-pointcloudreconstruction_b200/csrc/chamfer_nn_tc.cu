@@ -35,17 +35,19 @@
 namespace psd {
 namespace tc {
 
-constexpr int kScanWarps = 8;
+constexpr int kScanWarps = 16;                 // 4 per sub-partition: warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4).. of every tile
 constexpr int kMmaWarp = kScanWarps;            // warp index of the MMA issuer
-constexpr int kHelpWarps = 7;                   // 16 warps in all: 4 per sub-partition, 128 registers per thread
+constexpr int kHelpWarps = 7;                   // 24 warps in all: 6 per sub-partition, 80 registers per thread
 constexpr int kHelpThreads = kHelpWarps * 32;
 constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
-constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 512
+constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 768
+constexpr int kColGroups = kScanWarps / 4;      // column groups of a tile (one scanner warp per lane quarter and group)
 constexpr int kTileN = 256;                     // targets per MMA tile = TMEM buffer width (columns)
 constexpr int kBufs = 512 / kTileN;             // TMEM buffers: all 512 columns.  Two 256-column tiles beat four 128-column
                                                 // ones (37.4 vs 41.5 us at B=32, N=M=2048): the mbarrier / tcgen05.commit round
                                                 // trip per tile (~300-400 cycles, tools/ubench_pipe.cu) is paid half as often
 constexpr int kBufShift = 1;                    // log2(kBufs)
+constexpr int kGroupCols = kTileN / kColGroups; // 64 columns = one tmem_ld64_wait per tile and scanner warp
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
 constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value
@@ -55,15 +57,16 @@ constexpr float kQMax = 4096.0f;                // scaled |q-c| above this sends
 constexpr int kOffB = 0;                                  // [2][kMaxT/8][2][8][16 B]
 constexpr int kOffA = kOffB + 2 * kMaxT * 32;             // [2][16][2][8][16 B]
 constexpr int kOffRaw = kOffA + 2 * kQB * 32;             // [2][3][kMaxT] raw target coordinates (SoA), by B buffer
-constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][2 column groups][3][128]
-constexpr int kOffSq = kOffPart + 2 * 2 * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
+constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][kColGroups][3][128]
+constexpr int kOffSq = kOffPart + 2 * kColGroups * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
 constexpr int kFbCap = 512;                               // deferred exact-scan list (entries: unit << 8 | query)
 constexpr int kOffFb = kOffSq + 3 * 3 * kQB * 4;
-constexpr int kOffStat = kOffFb + kFbCap * 4;             // [16] wmax, [16] bad, [16] cmax, [2] group resident in sraw[i]
-constexpr int kOffBar = kOffStat + 3 * 16 * 4 + 16;       // 12 mbarriers (8-byte aligned)
+constexpr int kOffStat = kOffFb + kFbCap * 4;             // [32] wmax, [32] bad, [32] cmax (one per warp), [2] group resident in sraw[i]
+constexpr int kOffBar = kOffStat + 3 * 32 * 4 + 16;       // 12 mbarriers (8-byte aligned)
 constexpr int kOffMisc = kOffBar + 16 * 8;                // tmem base, nfb, abort
 constexpr int kSmemTC = kOffMisc + 64;
-static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8, "shared-memory carve-up alignment");
+static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8 && kThreadsTC / 32 <= 32 &&
+              kSmemTC <= 227 * 1024, "shared-memory carve-up");
 
 __device__ unsigned long long g_fallback_queries_tc = 0ull;
 
@@ -313,9 +316,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     int *fb_list = reinterpret_cast<int *>(smem + kOffFb);
     int *s_nfb = reinterpret_cast<int *>(smem + kOffMisc) + 1;
     float *s_wstat = reinterpret_cast<float *>(smem + kOffStat);
-    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + 16;
-    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 32;
-    int *s_rawgroup = reinterpret_cast<int *>(smem + kOffStat) + 48;   // cloud/direction whose raw targets sraw[i] holds
+    int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + 32;
+    float *s_cstat = reinterpret_cast<float *>(smem + kOffStat) + 64;
+    int *s_rawgroup = reinterpret_cast<int *>(smem + kOffStat) + 96;   // cloud/direction whose raw targets sraw[i] holds
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffMisc);
     volatile int *s_abort = reinterpret_cast<volatile int *>(smem + kOffMisc) + 2;
     const uint32_t sB_addr = smem_u32(smem + kOffB), sA_addr = smem_u32(smem + kOffA);
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     long long *pf = (DBG && prof) ? prof + (long long)blockIdx.x * 64 : nullptr;
     auto stamp = [&](int slot) { if (DBG && pf && slot < 56) pf[slot] = clock64(); };
     if (tid == 0) stamp(0);
+    zero_fill(p);
 
     if (tid == 0) {
         for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, kScanWarps); }
@@ -441,6 +445,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     // ---------------- prologue: the B operand of the first unit is built by the WHOLE CTA (everybody is idle anyway)
     Frame fr0 = {0.f, 0.f, 0.f, 1.f, 0.f, 0, 0};
     int group0 = -1;
+    float pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;   // helpers, threads < 128: raw query of the unit being staged, loaded early
     if (nunits > 0) {
         const Unit u = decode_unit(p, blk_begin);
         const NNDirection &D = p.dir[u.d];
@@ -449,6 +454,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 #pragma unroll
         for (int comp = 0; comp < 3; ++comp)
             for (int k = tid; k < u.nt; k += kThreadsTC) cp_async4(sraw + comp * kMaxT + k, tb + k * D.t_ps + comp * D.t_cs);
+        if (tid >= kHelp0 && tid - kHelp0 < kQB) {
+            // the queries of unit 0 travel together with its targets: one global round trip on the critical path, not two
+            int j = D.q_begin + u.qblock * kQB + (tid - kHelp0);
+            const int q_last = D.q_begin + D.q_count - 1;
+            j = j < q_last ? j : q_last;
+            const float *qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
+            pq1 = __ldg(qp); pq2 = __ldg(qp + D.q_cs); pq3 = __ldg(qp + 2 * D.q_cs);
+        }
         cp_async_wait_all();
         __syncthreads();
         build_b(u.nt, 0, tid, kThreadsTC, warp, [] { __syncthreads(); }, fr0);
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 
     if (warp < kScanWarps) {
         // ================================================= scanners
-        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column half of every tile
+        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column group of every tile
         const int row = r * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(r * 32) << 16);
         int g0 = 0;
@@ -479,7 +492,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 best = fminf(best, m);
                 bchunk = lt ? cid : bchunk;
             };
-            // every scanner warp takes its half (columns c*128 .. c*128+127) of every 256-column tile
+            // every scanner warp takes its column group (columns c*64 .. c*64+63) of every 256-column tile: ONE pair of loads per
+            // tile; the TMEM buffer is handed back as soon as they have landed, before any of the min work, so the MMA of tile
+            // t + 2 overlaps the reduction of tile t.  Four scanner warps per sub-partition hide the TMEM load latency and the
+            // mbarrier round trip behind each other's min work (tools/ubench_pipe.cu: 400 cycles per tile in this form).
             for (int t = 0; t < ntiles; ++t) {
                 const int gg = g0 + t;
                 const int b = gg & (kBufs - 1);
@@ -487,11 +503,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 mbar_wait(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
                 if (DBG) a59 += clock64() - w0;
                 tc_fence_after();
-                const int col0 = c * 128;                              // first column of this warp's share of the tile
+                const int col0 = c * kGroupCols;                       // first column of this warp's share of the tile
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN + col0);
                 const int cid0 = (t * kTileN + col0) / kCh;            // chunk id of the first 32 columns
                 uint32_t ra[32], rb[32];
                 tmem_ld64_wait(ta, ra, rb);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * b);
                 if (DBG && dbg) {
                     float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0;
 #pragma unroll
@@ -499,22 +518,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 }
                 chunk(ra, cid0);
                 chunk(rb, cid0 + 1);
-                tmem_ld64_wait(ta + 64, ra, rb);
-                // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * b);
-                if (DBG && dbg) {
-                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
-                }
-                chunk(ra, cid0 + 2);
-                chunk(rb, cid0 + 3);
             }
             g0 += ntiles;
             {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
-                float *pp = part + ((ul & 1) * 2 + c) * 3 * kQB;
+                float *pp = part + ((ul & 1) * kColGroups + c) * 3 * kQB;
                 pp[row] = best; pp[kQB + row] = second; reinterpret_cast<int *>(pp)[2 * kQB + row] = bchunk;
             }
             __syncwarp();
@@ -561,7 +568,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         const int ht = tid - kHelp0, hw = warp - (kScanWarps + 1);
         int st_group = group0, st_bsel = 0;  // cloud/direction of the most recently staged B operand; its buffer
         Frame fr_st = fr0;                   // frame of the most recently staged unit
-        float pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;   // raw query of the unit being staged (threads < 128), loaded early
         bool need_b = false;
 
         // does staging unit ul replace the B operand?  (uniform)
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         // cloud/direction is not the staged one, its raw targets into sraw[other buffer] by cp.async.
         auto stage_issue = [&](int ul, const Unit &u) {
             const NNDirection &D = p.dir[u.d];
-            if (ht < kQB) {
+            if (ht < kQB && ul > 0) {   // (unit 0's queries were loaded in the prologue)
                 int j = D.q_begin + u.qblock * kQB + ht;
                 const int q_last = D.q_begin + D.q_count - 1;
                 j = j < q_last ? j : q_last;
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         auto resolve = [&](int ul, const Unit &u, const Frame &fr) {
             const NNDirection &D = p.dir[u.d];
             const int nt = u.nt;
-            const float *pp = part + (ul & 1) * 2 * 3 * kQB;
+            const float *pp = part + (ul & 1) * kColGroups * 3 * kQB;
             const float *sqp = sq + (ul % 3) * 3 * kQB;
             const float *rx = sraw + (fr.bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
             const int q0 = hw * kQW;
@@ -637,7 +643,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             float b1 = kBig, b2 = kBig;
             int bc = 0;
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
+            for (int w = 0; w < kColGroups; ++w) {
                 const float v = pp[w * 3 * kQB + ql];
                 b2 = fminf(b2, fminf(pp[w * 3 * kQB + kQB + ql], fmaxf(b1, v)));
                 if (v < b1) { b1 = v; bc = reinterpret_cast<const int *>(pp)[w * 3 * kQB + 2 * kQB + ql]; }
@@ -645,18 +651,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const float x1 = sqp[ql], y1 = sqp[kQB + ql], z1 = sqp[2 * kQB + ql];
             const float ux = (x1 - fr.cx) * fr.cs, uy = (y1 - fr.cy) * fr.cs, uz = (z1 - fr.cz) * fr.cs;   // scaled frame
             const float qq = __fmaf_rn(uz, uz, __fmaf_rn(ux, ux, uy * uy));
-            // Filter error bound E = 15u*S (u = 2^-24): frame 2u, |t'|^2 3u, operand splits 6u (3*2^-22 |q'||t'| and
-            // |q'||t'| <= S/2), tensor-core accumulation 4u (measured total on B200: <= 4.1u, tools/tc_calibrate.py).  The
-            // reference's argmin lies in the best chunk if second > best + 2E + 10u*S = 40u*S.
-            //   S  = (|q'| + max|t'|)^2 bounds every target,
-            //   S' = (2|q'| + rho)^2 bounds the targets that can compete (within rho of the query).
+            // Filter error bound (u = 2^-24).  RELATIVE part E_r = 15u*S: frame 2u, |t'|^2 3u, operand splits 6u
+            // (3*2^-22 |q'||t'| and |q'||t'| <= S/2), tensor-core accumulation 4u (measured total on B200: <= 4.1u,
+            // tools/tc_calibrate.py).  ABSOLUTE part: the lo term of a split is an fp16 SUBNORMAL whenever |x| < 1/4
+            // (2^-12 |x| < 2^-14), so hi + lo = x only up to 2^-25 per coordinate (and |t'|^2's three terms up to 2^-25):
+            // E_a <= 2^-25 (sqrt(3) (|q'| + |t'|) + 1) with |q'| = 2|u|, |t'| <= |u| + rho for every target that can compete.
+            // The reference's argmin lies in the best chunk if second > best + 2 E_r + 10u*S + 2 E_a:
+            //   S  = (|u| + max|t'|)^2 bounds every target,
+            //   S' = (2|u| + rho)^2 bounds the targets that can compete (within rho of the query),
+            //   margin = 40u min(S, S') + 2^-24 (1 + 5.2|u| + 1.74 rho)       [coded with 25 % slack on the absolute part].
+            // Without the absolute part a query close to the frame centre (S' ~ 1e-5) trusted filter values whose fp16 operand
+            // error was 100x its margin: found by tests/test_gpu_tc_hypothesis.py, reproduced on the CPU by
+            // tools/tc_filter_model.py (6 591 wrong chunks in 129 k adversarial queries without the term, 0 with it; the
+            // exact-scan fallback rate on U[0,1)^3 is unchanged).
             const float qn = sqrtf(qq);
             const float rr = qn + sqrtf(fr.wmax);
             const float S = rr * rr;
-            const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 1.5e-6f * S);
+            const float rho = sqrtf(fmaxf(b1 + qq, 0.f) + 2.0e-6f * S);
             const float r2 = 2.0f * qn + rho;
             const float Seff = fminf(S, r2 * r2);
-            const float margin = __fmaf_rn(Seff, 2.5e-6f, 1e-36f);
+            const float margin = __fmaf_rn(Seff, 2.5e-6f, 1.5e-7f * (0.5f + __fmaf_rn(2.6f, qn, 0.9f * rho)));
             const bool ok = live && !fr.bad && (qn < kQMax) && (b2 > b1 + margin);
             float ws = 0.f;   // fused epilogue accumulators of this lane
             int wc = 0;

@@ -10,7 +10,8 @@
 // launchers implemented in chamfer.cu / emd.cu
 cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout,
                                        float *dist1, float *dist2, int *idx1, int *idx2, float *sums, float fs_thr,
-                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream);
+                                       int *fs_count, int q_begin, int q_count, cudaStream_t stream, float *zero_buf = nullptr,
+                                       long long zero_floats = 0);
 cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                         const float *graddist1, const float *graddist2, const int *idx1, const int *idx2,
                                         int b, int n, int m, int layout, int overwrite, cudaStream_t stream,
@@ -26,7 +27,6 @@ int psd_icp_max_points();
 int psd_set_emd_solo(int enable);
 int psd_set_emd_grid(int enable);
 int psd_set_tc_max_ctas(int n);
-int psd_set_grad_mode(int split, int max_ctas);
 cudaError_t psd_launch_cont_proj(const float *pcl, int b, int n, int grid_h, int grid_w, float sigma_sq, float *out,
                                  cudaStream_t stream);
 cudaError_t psd_launch_cont_proj_backward(const float *pcl, const float *gout, int b, int n, int grid_h, int grid_w,
@@ -108,6 +108,18 @@ int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, i
     return finish("psd_chamfer_forward_ex",
                   psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums, fs_thr,
                                              fs_count, q_begin, q_count, (cudaStream_t)stream));
+}
+
+int psd_chamfer_forward_zero(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                             float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, float *zero_buf,
+                             long long zero_floats, void *stream) {
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_forward_zero: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
+        return -1;
+    }
+    return finish("psd_chamfer_forward_zero",
+                  psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums, fs_thr,
+                                             fs_count, 0, -1, (cudaStream_t)stream, zero_buf, zero_floats));
 }
 
 int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
@@ -212,6 +224,19 @@ int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, i
     return finish("psd_chamfer_mean_loss_forward", e);
 }
 
+int psd_chamfer_mean_loss_forward_zero(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                                       float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, float *zero_buf,
+                                       long long zero_floats, void *stream) {
+    if (layout < 0 || layout > 3) {
+        psd_set_error_msg("psd_chamfer_mean_loss_forward_zero: layout is a bit mask: 1 = xyz1 is [B,3,N], 2 = xyz2 is [B,3,M]");
+        return -1;
+    }
+    cudaError_t e = psd_launch_chamfer_forward(xyz1, xyz2, b, n, m, layout, dist1, dist2, idx1, idx2, sums_zeroed, 0.f, nullptr,
+                                               0, -1, (cudaStream_t)stream, zero_buf, zero_floats);
+    if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(sums_zeroed, b, n, m, loss, (cudaStream_t)stream);
+    return finish("psd_chamfer_mean_loss_forward_zero", e);
+}
+
 int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                    const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream) {
     return finish("psd_chamfer_mean_loss_backward",
@@ -283,8 +308,6 @@ int psd_emd_solo_mode(int enable) { return psd_set_emd_solo(enable); }
 int psd_emd_grid_mode(int enable) { return psd_set_emd_grid(enable); }
 
 int psd_chamfer_tc_ctas(int max_ctas) { return psd_set_tc_max_ctas(max_ctas); }
-
-int psd_chamfer_grad_mode(int split, int max_ctas) { return psd_set_grad_mode(split, max_ctas); }
 
 int psd_debug_tc_prof(long long *prof_dev) { psd_set_tc_prof(prof_dev); return 1; }
 
@@ -380,11 +403,15 @@ static cudaError_t enqueue_loss_step(const StepArgs &a, float *ws, cudaStream_t 
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_x2, a.x2, sizeof(float) * 3 * s2, cudaMemcpyHostToDevice, stream);
     }
     if (e != cudaSuccess) return e;
-    // per-cloud sums start from zero; the gradients need no initialisation (two-phase backward)
+    // per-cloud sums start from zero (one small memset); the gradients are zero-filled by the forward launch itself when they
+    // sit in the workspace (grad1 | grad2 adjacent), so the backward is the single accumulate launch
     if ((e = cudaMemsetAsync(d_sums, 0, sizeof(float) * (2 * (size_t)b + 1), stream)) != cudaSuccess) return e;
-    e = psd_launch_chamfer_forward(x1, d_x2, b, n, m, layout, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream);
+    const bool own_g1 = (g1 == d_g1);
+    if (!own_g1 && (e = cudaMemsetAsync(g1, 0, sizeof(float) * 3 * s1, stream)) != cudaSuccess) return e;
+    e = psd_launch_chamfer_forward(x1, d_x2, b, n, m, layout, d_d1, d_d2, d_i1, d_i2, d_sums, 0.f, nullptr, 0, -1, stream,
+                                   own_g1 ? d_g1 : d_g2, (long long)(own_g1 ? 3 * (s1 + s2) : 3 * s2));
     if (e == cudaSuccess) e = psd_launch_chamfer_mean_loss(d_sums, b, n, m, d_loss, stream);
-    if (e == cudaSuccess) e = psd_launch_chamfer_backward(x1, d_x2, g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, layout, 1, stream, nullptr);
+    if (e == cudaSuccess) e = psd_launch_chamfer_backward(x1, d_x2, g1, d_g2, nullptr, nullptr, d_i1, d_i2, b, n, m, layout, 0, stream, nullptr);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync(a.loss_host, d_loss, sizeof(float), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess && a.g1_host) e = cudaMemcpyAsync(a.g1_host, g1, sizeof(float) * 3 * s1, cudaMemcpyDeviceToHost, stream);

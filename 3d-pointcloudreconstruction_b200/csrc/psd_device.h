@@ -30,7 +30,6 @@ struct DeviceState {
     int device = -1;
     int num_sms = 0, max_smem = 0;
     bool attr_nn = false, attr_tc = false, attr_proj = false;   // dynamic shared-memory opt-ins done on this device
-    int grad_ctas_per_sm = 0;                                   // co-resident CTAs of the cooperative backward kernel
     float *fwd_ws = nullptr;                                    // psd_chamfer_forward_host staging
     size_t fwd_ws_bytes = 0;
     float *step_ws[kStepSlots] = {};                            // psd_chamfer_loss_step_host_ex staging, by slot

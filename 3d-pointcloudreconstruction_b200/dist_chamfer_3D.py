@@ -35,12 +35,16 @@ def as_kernel_cloud(t):
     return t, lay
 
 
-def grad_buffer_like(t, lay):
-    """Uninitialised gradient with the memory layout of its cloud, seen as [B,N,3]."""
-    if lay == 1:
-        b, n, _ = t.shape
-        return torch.empty(b, 3, n, device=t.device, dtype=torch.float32).transpose(1, 2)
-    return torch.empty(t.shape, device=t.device, dtype=torch.float32)
+def grad_buffers(xyz1, xyz2, layout, zero=False):
+    """One allocation for both gradients (adjacent, so that one fill covers them); each is returned as a [B,N,3] view with the
+    memory layout of its cloud.  Returns (flat buffer, grad1, grad2)."""
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    flat = (torch.zeros if zero else torch.empty)(3 * b * (n + m), device=xyz1.device, dtype=torch.float32)
+    g1, g2 = flat[: 3 * b * n], flat[3 * b * n:]
+    g1 = g1.view(b, 3, n).transpose(1, 2) if layout & 1 else g1.view(b, n, 3)
+    g2 = g2.view(b, 3, m).transpose(1, 2) if layout & 2 else g2.view(b, m, 3)
+    return flat, g1, g2
 
 
 class chamfer_3DFunction(Function):
@@ -67,10 +71,14 @@ class chamfer_3DFunction(Function):
         idx2 = torch.empty(batchsize, m, device=device, dtype=torch.int32)
         if n == 0 or m == 0 or batchsize == 0:  # the reference leaves its zero-filled outputs untouched
             dist1.zero_(); dist2.zero_(); idx1.zero_(); idx2.zero_()
+        # the gradient buffers of a backward that may follow are zero-filled by the forward launch itself (the reference
+        # zero-fills them on the CPU and copies, dist_chamfer_3D.py:62-66): no memset on the way back
+        ctx.grads = grad_buffers(xyz1, xyz2, layout) if any(ctx.needs_input_grad) else None
         with torch.cuda.device(device):
-            rc = _lib.lib.psd_chamfer_forward_ex(_lib.ptr(xyz1), _lib.ptr(xyz2), batchsize, n, m, layout, _lib.ptr(dist1),
-                                                 _lib.ptr(dist2), _lib.ptr(idx1), _lib.ptr(idx2), None, 0.0, None, 0, -1,
-                                                 _lib.stream_of(xyz1))
+            rc = _lib.lib.psd_chamfer_forward_zero(_lib.ptr(xyz1), _lib.ptr(xyz2), batchsize, n, m, layout, _lib.ptr(dist1),
+                                                   _lib.ptr(dist2), _lib.ptr(idx1), _lib.ptr(idx2), None, 0.0, None,
+                                                   _lib.ptr(ctx.grads[0]) if ctx.grads else None,
+                                                   ctx.grads[0].numel() if ctx.grads else 0, _lib.stream_of(xyz1))
         if rc != 1:
             raise RuntimeError(f"chamfer_3D.forward failed (rc={rc}): {_lib.last_error()}")
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
@@ -86,13 +94,13 @@ class chamfer_3DFunction(Function):
         m = xyz2.shape[1]
         graddist1 = graddist1.contiguous()
         graddist2 = graddist2.contiguous()
-        # no zero fill: the two-phase backward kernel stores every element once, then adds the scatter terms
-        gradxyz1 = grad_buffer_like(xyz1, layout & 1)
-        gradxyz2 = grad_buffer_like(xyz2, (layout >> 1) & 1)
+        # buffers the forward launch zero-filled; a second backward through the same graph gets fresh zeros
+        grads, ctx.grads = ctx.grads, None
+        _, gradxyz1, gradxyz2 = grads if grads is not None else grad_buffers(xyz1, xyz2, layout, zero=True)
         with torch.cuda.device(xyz1.device):
             rc = _lib.lib.psd_chamfer_backward_ex(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(gradxyz1), _lib.ptr(gradxyz2),
                                                   _lib.ptr(graddist1), _lib.ptr(graddist2), _lib.ptr(idx1), _lib.ptr(idx2),
-                                                  b, n, m, layout, 1, _lib.stream_of(xyz1))
+                                                  b, n, m, layout, 0, _lib.stream_of(xyz1))
         if rc != 1:
             raise RuntimeError(f"chamfer_3D.backward failed (rc={rc}): {_lib.last_error()}")
         return gradxyz1, gradxyz2

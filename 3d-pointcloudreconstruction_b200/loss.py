@@ -3,20 +3,20 @@ import torch
 import torch.nn as nn
 
 try:
-    from .dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffer_like
+    from .dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffers
     from . import emd_module as emd_func
     from . import _lib
 except ImportError:
-    from dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffer_like
+    from dist_chamfer_3D import chamfer_3DDist, as_kernel_cloud, grad_buffers
     import emd_module as emd_func
     import _lib
 
 
 class _ChamferMeanLoss(torch.autograd.Function):
     """mean(dist1) + mean(dist2) (loss/loss.py:35-36) as ONE forward launch (+ a one-warp reduction) and ONE backward
-    launch: the per-cloud sums come from the NN kernel's epilogue and the constant gradients 1/(B*N), 1/(B*M) are formed
-    inside the backward kernel (psd_chamfer_mean_loss_forward / _backward_ex), which stores the gradients without a zero
-    fill.  Clouds are read in place as [B,N,3] or as the transposed view of a [B,3,N] tensor (train.py:163).  Results agree
+    launch: the per-cloud sums come from the NN kernel's epilogue, the same launch zero-fills the gradient buffers, and the
+    constant gradients 1/(B*N), 1/(B*M) are formed inside the backward kernel (psd_chamfer_mean_loss_forward_zero /
+    _backward_ex) -- no memset, no gradient tensors.  Clouds are read in place as [B,N,3] or as the transposed view of a [B,3,N] tensor (train.py:163).  Results agree
     with the unfused path to fp32 summation-order noise (the sums are accumulated with float atomics)."""
 
     @staticmethod
@@ -31,12 +31,14 @@ class _ChamferMeanLoss(torch.autograd.Function):
         ibuf = torch.empty(b * (n + m), device=dev, dtype=torch.int32)
         small = torch.zeros(2 * b + 1, device=dev, dtype=torch.float32)      # per-cloud sums [B,2] + the loss scalar
         idx1, idx2 = ibuf[: b * n], ibuf[b * n:]
+        ctx.grads = grad_buffers(xyz1, xyz2, layout) if any(ctx.needs_input_grad) else None
         with torch.cuda.device(dev):
-            rc = _lib.lib.psd_chamfer_mean_loss_forward(
+            rc = _lib.lib.psd_chamfer_mean_loss_forward_zero(
                 _lib.ptr(xyz1), _lib.ptr(xyz2), b, n, m, layout, _lib.ptr(fbuf), _lib.ptr(fbuf[b * n:]), _lib.ptr(idx1),
-                _lib.ptr(idx2), _lib.ptr(small), _lib.ptr(small[2 * b:]), _lib.stream_of(xyz1))
+                _lib.ptr(idx2), _lib.ptr(small), _lib.ptr(small[2 * b:]), _lib.ptr(ctx.grads[0]) if ctx.grads else None,
+                ctx.grads[0].numel() if ctx.grads else 0, _lib.stream_of(xyz1))
         if rc != 1:
-            raise RuntimeError(f"psd_chamfer_mean_loss_forward failed (rc={rc}): {_lib.last_error()}")
+            raise RuntimeError(f"psd_chamfer_mean_loss_forward_zero failed (rc={rc}): {_lib.last_error()}")
         ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
         ctx.layout = layout
         return small[2 * b]
@@ -48,11 +50,11 @@ class _ChamferMeanLoss(torch.autograd.Function):
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         up = grad_loss.contiguous().to(torch.float32)
-        g1 = grad_buffer_like(xyz1, layout & 1)
-        g2 = grad_buffer_like(xyz2, (layout >> 1) & 1)
+        grads, ctx.grads = ctx.grads, None        # zero-filled by the forward launch; a second backward gets fresh zeros
+        _, g1, g2 = grads if grads is not None else grad_buffers(xyz1, xyz2, layout, zero=True)
         with torch.cuda.device(xyz1.device):
             rc = _lib.lib.psd_chamfer_mean_loss_backward_ex(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(g1), _lib.ptr(g2),
-                                                            _lib.ptr(up), _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, layout, 1,
+                                                            _lib.ptr(up), _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, layout, 0,
                                                             _lib.stream_of(xyz1))
         if rc != 1:
             raise RuntimeError(f"psd_chamfer_mean_loss_backward_ex failed (rc={rc}): {_lib.last_error()}")

@@ -57,6 +57,14 @@ int psd_chamfer_forward_ex(const float *xyz1, const float *xyz2, int b, int n, i
                            float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, int q_begin,
                            int q_count, void *stream);
 
+/* psd_chamfer_forward_ex over all queries that ALSO zero-fills zero_buf[0 .. zero_floats) inside the same launch (a few
+ * stores per thread before the search starts): pass the gradient buffers that the backward following on the stream will
+ * accumulate into and the step needs no memset (the reference's wrapper zero-fills them on the CPU and copies,
+ * dist_chamfer_3D.py:62-66).  zero_buf may be NULL. */
+int psd_chamfer_forward_zero(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                             float *dist2, int *idx1, int *idx2, float *sums, float fs_thr, int *fs_count, float *zero_buf,
+                             long long zero_floats, void *stream);
+
 /* Replaces chamfer_3D.backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
  *   = chamfer_backward, metric/chamfer3D/chamfer_cuda.cpp:22-26
  *   -> chamfer_cuda_backward, metric/chamfer3D/chamfer3D.cu:176-195 (two NmDistanceGradKernel launches).
@@ -68,9 +76,9 @@ int psd_chamfer_backward(const float *xyz1, const float *xyz2, float *gradxyz1, 
                          int m, void *stream);
 
 /* The same gradient with the layouts of psd_chamfer_forward_ex (a gradient has the layout of its cloud) and, with
- * overwrite != 0, WITHOUT the caller-zeroed contract: the kernel first stores every point's own term (each element of both
- * gradients exactly once), passes a grid-wide barrier (cooperative launch) and then adds the scatter terms -- no memset
- * before the launch and half the atomics.  overwrite == 0 accumulates like psd_chamfer_backward. */
+ * overwrite != 0, WITHOUT the caller-zeroed contract: a first launch stores every point's own term (each element of both
+ * gradients exactly once), a second one adds the scatter terms.  overwrite == 0 accumulates like psd_chamfer_backward;
+ * the cheapest step is overwrite == 0 on buffers that the FORWARD launch zero-filled (psd_chamfer_forward_zero). */
 int psd_chamfer_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                             const float *graddist1, const float *graddist2, const int *idx1, const int *idx2, int b, int n,
                             int m, int layout, int overwrite, void *stream);
@@ -138,6 +146,9 @@ int psd_emd_mean_loss_backward(const float *xyz1, const float *xyz2, float *grad
  * (see psd_chamfer_backward_ex).  Same return convention as above. */
 int psd_chamfer_mean_loss_forward(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
                                   float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, void *stream);
+int psd_chamfer_mean_loss_forward_zero(const float *xyz1, const float *xyz2, int b, int n, int m, int layout, float *dist1,
+                                       float *dist2, int *idx1, int *idx2, float *sums_zeroed, float *loss, float *zero_buf,
+                                       long long zero_floats, void *stream);   /* + the zero fill of psd_chamfer_forward_zero */
 int psd_chamfer_mean_loss_backward(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
                                    const float *upstream, const int *idx1, const int *idx2, int b, int n, int m, void *stream);
 int psd_chamfer_mean_loss_backward_ex(const float *xyz1, const float *xyz2, float *gradxyz1, float *gradxyz2,
@@ -264,13 +275,6 @@ int psd_emd_grid_mode(int enable);
  * half the SM count: every CTA then owns twice as many units, so its serial prologue and tail amortise, and the launch on
  * the other stream fills the remaining SMs.  Returns the previous value.  Results are identical. */
 int psd_chamfer_tc_ctas(int max_ctas);
-
-/* Form of the overwrite backward (psd_chamfer_backward_ex with overwrite != 0).  split: 0 = one cooperative launch with a
- * grid-wide barrier between the stores and the scatter atomics (default), 1 = two plain launches (stream order is the
- * barrier); max_ctas: upper bound on the cooperative grid (0 = as many 256-thread CTAs as are co-resident), for callers
- * that keep several launches in flight and do not want a backward to wait for most of the GPU.  Negative values only query.
- * Returns split | max_ctas << 1 as they were.  Results are identical in every form. */
-int psd_chamfer_grad_mode(int split, int max_ctas);
 
 /* Bring-up / calibration hook of the tensor-core kernel: runs psd_chamfer_forward on that kernel and additionally
  * dumps every raw filter value a_k (before the exact rescan) to dump[(unit*128 + row) * dump_ld + target], where a

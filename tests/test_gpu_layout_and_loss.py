@@ -82,6 +82,32 @@ def test_backward_overwrite_ignores_buffer_contents(pkg, oracle, cuda):
     assert lib.psd_chamfer_backward_ex(None, None, None, None, None, None, None, None, 1, 1, 1, 7, 1, None) == -1   # bad layout
 
 
+def test_second_backward_through_the_same_graph(pkg, oracle, cuda):
+    """The forward launch zero-fills the gradient buffers once; backward(retain_graph=True) twice must not accumulate the
+    first pass into the second (fresh zeros the second time), for the module and for the fused loss."""
+    x, y = make_clouds("uniform", 2, 300, 400, seed=4)
+    want = oracle.chamfer_forward(x, y)
+    g1 = np.full((2, 300), 1.0 / 600, np.float32); g2 = np.full((2, 400), 1.0 / 800, np.float32)
+    w1, w2 = oracle.chamfer_backward(x, y, g1, g2, want[2], want[3])
+    for fused in (False, True):
+        tx = torch.from_numpy(x).to(cuda).requires_grad_(True)
+        ty = torch.from_numpy(y).to(cuda).requires_grad_(True)
+        if fused:
+            loss = pkg.Loss().get_chamfer_loss(tx, ty)
+        else:
+            d1, d2, _, _ = pkg.chamfer_3DDist()(tx, ty)
+            loss = d1.mean() + d2.mean()
+        (a1, a2) = torch.autograd.grad(loss, (tx, ty), retain_graph=True)
+        a1, a2 = a1.clone(), a2.clone()
+        (b1, b2) = torch.autograd.grad(loss, (tx, ty))
+        for got, w in ((a1, w1), (b1, w1), (a2, w2), (b2, w2)):
+            assert np.abs(got.cpu().numpy() - w).max() <= 1e-5 * np.abs(w).max(), fused
+    # no gradient wanted: no buffer is allocated or filled
+    with torch.no_grad():
+        out = pkg.chamfer_3DDist()(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda))
+    assert np.array_equal(out[2].cpu().numpy(), want[2])
+
+
 def test_loss_chamfer_on_transposed_prediction(pkg, oracle, cuda):
     """Loss.get_chamfer_loss(fake.transpose(2,1), points) -- train.py:163 verbatim -- on the fused path without a copy."""
     b, n = 4, 1024

@@ -39,7 +39,7 @@ def adversarial_cloud(kind, rng, b, n):
     return np.ascontiguousarray(p, np.float32)
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(kind_q=st.sampled_from(KINDS), kind_t=st.sampled_from(KINDS + ("same",)), b=st.integers(1, 5), n=st.integers(1, 2600),
        m=st.integers(1, 2600), seed=st.integers(0, 2 ** 31 - 1))
 def test_tensor_core_kernel_sweep(pkg, oracle, cuda, kind_q, kind_t, b, n, m, seed):
@@ -51,17 +51,18 @@ def test_tensor_core_kernel_sweep(pkg, oracle, cuda, kind_q, kind_t, b, n, m, se
         y[:, :k] = x[:, :k]
     else:
         y = adversarial_cloud(kind_t, rng, b, m)
-    old = pkg._lib.lib.psd_chamfer_nn_variant(3)
-    try:
-        out = pkg.chamfer_3DDist()(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda))
-        torch.cuda.synchronize()
-    finally:
-        pkg._lib.lib.psd_chamfer_nn_variant(old)
     want = oracle.chamfer_forward(x, y, nthreads=8)
-    for got, w, name in zip(out, want, ("dist1", "dist2", "idx1", "idx2")):
-        g = got.cpu().numpy()
-        same = (g.view(np.uint32) == w.view(np.uint32)) if g.dtype == np.float32 else (g == w)
-        assert same.all(), f"{kind_q}/{kind_t} b={b} n={n} m={m} seed={seed}: {name} differs at {np.argwhere(~same)[:3].tolist()}"
+    for variant in (3, 1):              # the tensor-core kernel, and the FFMA kernel (same scheme, fp32 filter)
+        old = pkg._lib.lib.psd_chamfer_nn_variant(variant)
+        try:
+            out = pkg.chamfer_3DDist()(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda))
+            torch.cuda.synchronize()
+        finally:
+            pkg._lib.lib.psd_chamfer_nn_variant(old)
+        for got, w, name in zip(out, want, ("dist1", "dist2", "idx1", "idx2")):
+            g = got.cpu().numpy()
+            same = (g.view(np.uint32) == w.view(np.uint32)) if g.dtype == np.float32 else (g == w)
+            assert same.all(), f"variant {variant} {kind_q}/{kind_t} b={b} n={n} m={m} seed={seed}: {name} differs at {np.argwhere(~same)[:3].tolist()}"
 
 
 @pytest.mark.parametrize("kind", KINDS)

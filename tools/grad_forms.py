@@ -1,7 +1,7 @@
 """A/B of the chamfer backward forms at config 2 (B=32, N=M=2048), graph replay, CUDA events, L2-resident and HBM-cold:
   accumulate : torch zero fill + psd_chamfer_backward (all terms atomic; the reference's contract)
-  coop       : psd_chamfer_backward_ex(overwrite=1), one cooperative launch (store, grid barrier, scatter atomics)
-  split      : the same as two plain launches
+  fused zero : psd_chamfer_forward_zero (the forward launch zero-fills the gradients) + psd_chamfer_backward
+  overwrite  : psd_chamfer_backward_ex(overwrite=1): store launch + scatter launch
 and the forward + backward step in the serial form and with 8 chains x 37-CTA forward launches in flight."""
 import ctypes, os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,6 +26,10 @@ flush = torch.empty(64 * 1024 * 1024, device=dev)
 def fwd(p): assert pkg.chamfer_3D.forward(xs[p], ys[p], d1[p], d2[p], i1[p], i2[p]) == 1
 def bwd_acc(p):
     gb[p].zero_()
+    assert lib.psd_chamfer_backward(vp(xs[p]), vp(ys[p]), vp(gb[p][:3*B*N]), vp(gb[p][3*B*N:]), vp(gd1[p]), vp(gd2[p]), vp(i1[p]), vp(i2[p]), B, N, N, cur()) == 1
+def fwd_zero(p):
+    assert lib.psd_chamfer_forward_zero(vp(xs[p]), vp(ys[p]), B, N, N, 0, vp(d1[p]), vp(d2[p]), vp(i1[p]), vp(i2[p]), None, 0.0, None, vp(gb[p]), gb[p].numel(), cur()) == 1
+def bwd_acc_nozero(p):
     assert lib.psd_chamfer_backward(vp(xs[p]), vp(ys[p]), vp(gb[p][:3*B*N]), vp(gb[p][3*B*N:]), vp(gd1[p]), vp(gd2[p]), vp(i1[p]), vp(i2[p]), B, N, N, cur()) == 1
 def bwd_ow(p):
     assert lib.psd_chamfer_backward_ex(vp(xs[p]), vp(ys[p]), vp(gb[p][:3*B*N]), vp(gb[p][3*B*N:]), vp(gd1[p]), vp(gd2[p]), vp(i1[p]), vp(i2[p]), B, N, N, 0, 1, cur()) == 1
@@ -58,20 +62,14 @@ def timed(body, reps=48, chains=1, cold=True):
 for p in range(pool): fwd(p)
 torch.cuda.synchronize()
 print(f"forward alone (serial)            : {timed(fwd):7.2f} us")
-for name, split, fn in (("accumulate (zero fill + atomics)", -1, bwd_acc), ("coop (one launch)", 0, bwd_ow), ("split (two launches)", 1, bwd_ow)):
-    lib.psd_chamfer_grad_mode(split, 0)
+print(f"forward + fused zero fill         : {timed(fwd_zero):7.2f} us")
+for name, fn in (("accumulate (zero fill + atomics)", bwd_acc), ("accumulate, pre-zeroed buffers", bwd_acc_nozero), ("overwrite (two launches)", bwd_ow)):
     print(f"backward {name:32s}: {timed(fn):7.2f} us cold, {timed(fn, cold=False):7.2f} us warm")
-for cap in (296, 148, 74):
-    lib.psd_chamfer_grad_mode(0, cap)
-    print(f"backward coop, grid <= {cap:4d}          : {timed(bwd_ow):7.2f} us cold")
-lib.psd_chamfer_grad_mode(0, 0)
-for name, split, cap, fn in (("accumulate", -1, 0, bwd_acc), ("coop", 0, 0, bwd_ow), ("coop<=148", 0, 148, bwd_ow), ("coop<=74", 0, 74, bwd_ow), ("split", 1, 0, bwd_ow)):
-    lib.psd_chamfer_grad_mode(split, cap)
-    step = lambda p, fn=fn: (fwd(p), fn(p))
+for name, f, bk in (("memset + accumulate", fwd, bwd_acc), ("fused zero + accumulate", fwd_zero, bwd_acc_nozero), ("overwrite", fwd, bwd_ow)):
+    step = lambda p, f=f, bk=bk: (f(p), bk(p))
     lib.psd_chamfer_tc_ctas(0)
     ser = timed(step)
     lib.psd_chamfer_tc_ctas(37)
     pip = timed(step, reps=48, chains=8)
     lib.psd_chamfer_tc_ctas(0)
-    print(f"step fwd+bwd, backward = {name:10s}: serial {ser:7.2f} us, 8 chains x 37 CTAs {pip:7.2f} us")
-lib.psd_chamfer_grad_mode(0, 0)
+    print(f"step fwd+bwd, {name:24s}: serial {ser:7.2f} us, 8 chains x 37 CTAs {pip:7.2f} us")

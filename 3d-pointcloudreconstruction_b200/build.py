@@ -23,13 +23,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """out / defines: A/B builds of the same ABI (loaded through the PSD_B200_LIB environment variable)."""
+    if out == OUT and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = ([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out] +
+           [os.path.join(CSRC, s) for s in SOURCES])
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 PYBIND_DIR = os.path.join(HERE, "pybind")

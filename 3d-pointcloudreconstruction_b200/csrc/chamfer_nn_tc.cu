@@ -35,9 +35,15 @@
 namespace psd {
 namespace tc {
 
-constexpr int kScanWarps = 16;                 // 4 per sub-partition: warp w reads TMEM lanes 32*(w%4).., columns 64*(w/4).. of every tile
+#ifndef PSD_TC_SCAN_WARPS
+#define PSD_TC_SCAN_WARPS 8                     // 8 (two per sub-partition, 128 columns each); A/B builds: 16 (four, 64 columns each)
+#endif
+#ifndef PSD_TC_SETMAXNREG
+#define PSD_TC_SETMAXNREG (PSD_TC_SCAN_WARPS == 16)
+#endif
+constexpr int kScanWarps = PSD_TC_SCAN_WARPS;   // warp w reads TMEM lanes 32*(w%4).., column group w/4 of every tile
 constexpr int kMmaWarp = kScanWarps;            // warp index of the MMA issuer
-constexpr int kHelpWarps = 7;                   // 24 warps in all: 6 per sub-partition, 80 registers per thread
+constexpr int kHelpWarps = 7;                   // 24 (16) warps in all, 80 (128) registers per thread at launch
 constexpr int kHelpThreads = kHelpWarps * 32;
 constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
 constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 768
@@ -47,7 +53,7 @@ constexpr int kBufs = 512 / kTileN;             // TMEM buffers: all 512 columns
                                                 // ones (37.4 vs 41.5 us at B=32, N=M=2048): the mbarrier / tcgen05.commit round
                                                 // trip per tile (~300-400 cycles, tools/ubench_pipe.cu) is paid half as often
 constexpr int kBufShift = 1;                    // log2(kBufs)
-constexpr int kGroupCols = kTileN / kColGroups; // 64 columns = one tmem_ld64_wait per tile and scanner warp
+constexpr int kGroupCols = kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
 constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value
@@ -62,7 +68,7 @@ constexpr int kOffSq = kOffPart + 2 * kColGroups * 3 * kQB * 4;    // [3][3][128
 constexpr int kFbCap = 512;                               // deferred exact-scan list (entries: unit << 8 | query)
 constexpr int kOffFb = kOffSq + 3 * 3 * kQB * 4;
 constexpr int kOffStat = kOffFb + kFbCap * 4;             // [32] wmax, [32] bad, [32] cmax (one per warp), [2] group resident in sraw[i]
-constexpr int kOffBar = kOffStat + 3 * 32 * 4 + 16;       // 12 mbarriers (8-byte aligned)
+constexpr int kOffBar = kOffStat + 3 * 32 * 4 + 16;       // 8 mbarriers (8-byte aligned)
 constexpr int kOffMisc = kOffBar + 16 * 8;                // tmem base, nfb, abort
 constexpr int kSmemTC = kOffMisc + 64;
 static_assert(kOffBar % 8 == 0 && kOffA % 128 == 0 && kOffRaw % 16 == 0 && kOffPart % 16 == 0 && kHelpWarps <= 8 && kThreadsTC / 32 <= 32 &&
@@ -100,6 +106,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
         }
     }
 }
+#ifndef PSD_TC_POLL_LANE0
+#define PSD_TC_POLL_LANE0 0
+#endif
+// warp-wide wait: every lane polls, or (A/B build) lane 0 polls and the warp reconverges behind it
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, volatile int *abort_flag) {
+    if (PSD_TC_POLL_LANE0) {
+        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, abort_flag);
+        __syncwarp();
+    } else {
+        mbar_wait(bar, parity, abort_flag);
+    }
+}
 __device__ __forceinline__ void cp_async4(void *smem_dst, const float *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -113,6 +131,15 @@ __device__ __forceinline__ void split_h(float x, unsigned short &hi, unsigned sh
     const __half h = __float2half_rn(x);
     const __half l = __float2half_rn(x - __half2float(h));
     hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+}
+// the same for two values at once with the PACKED conversion (F2FP.F16.F32.PACK_AB: one full-rate instruction for two
+// values; the scalar F2F.F16.F32 runs on the slow conversion path and bounded the operand build: 9 per target row)
+__device__ __forceinline__ void split_h2(float a, float b, unsigned short &ah, unsigned short &al, unsigned short &bh, unsigned short &bl) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    ah = __half_as_ushort(__low2half(h)); bh = __half_as_ushort(__high2half(h));
+    al = __half_as_ushort(__low2half(l)); bl = __half_as_ushort(__high2half(l));
 }
 __device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
 // K-major, no swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes, 8 fp16 per row); LBO = distance between
@@ -354,11 +381,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     const uint32_t tmem_base = *s_tmem;
     if (tid == 0) stamp(1);
 
-    // Build the B operand of a cloud/direction from its raw targets in sraw[bsel] (already landed and visible to the
-    // team): centre, power-of-two scale, scaled split fp16 rows.  Called by a team of tn threads (tt = index in the team,
-    // tw = warp index in the team) with its own barrier; returns the frame (statistics valid after the caller's next
-    // team barrier via s_wstat / s_bstat).
-    auto build_b = [&](int nt, int bsel, int tt, int tn, int tw, auto &&team_bar, Frame &fr) {
+    // The B operand of a cloud/direction is built from its raw targets in sraw[bsel] (already landed and visible to the team) in
+    // two steps.  frame_of: centre and power-of-two scale (one pass over the targets by a team of tn threads -- tt = index in
+    // the team, tw = warp index in the team -- with the team's own barrier).  build_rows: the scaled split fp16 rows of targets
+    // [k0, k1) (rows beyond nt are padding), accumulating the thread's max |t'|^2 and its bad flag.
+    auto frame_of = [&](int nt, int bsel, int tt, int tn, int tw, auto &&team_bar, Frame &fr, int &bad) {
         const float *rx = sraw + (bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
         float cx, cy, cz;
         {   // centre of the filter frame: mean of up to 8 evenly spaced targets (any value is correct)
@@ -375,9 +402,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const float inv = 1.0f / (float)ns;
             cx = sx * inv; cy = sy * inv; cz = sz * inv;
         }
-        // pass 1: extent around the centre -> power-of-two scale
+        // extent around the centre -> power-of-two scale
         float cmax = 0.f;
-        int bad = 0;
+        bad = 0;
 #pragma unroll 4
         for (int k = tt; k < nt; k += tn) {
             const float ax = fabsf(rx[k] - cx), ay = fabsf(ry[k] - cy), az = fabsf(rz[k] - cz);
@@ -399,26 +426,27 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             e = e < 27 ? 27 : (e > 227 ? 227 : e);                   // keep s within [2^-101, 2^99]
             cs = cmax > 0.f ? __uint_as_float((uint32_t)(253 - e) << 23) : 1.0f;   // 2^(126 - e): s*cmax in [0.5, 1)
         }
-        // pass 2: scaled, split B operand
-        const int npad = ((nt + kTileN - 1) / kTileN) * kTileN;
-        float wmax = 0.f;
-        unsigned char *sBb = smem + kOffB + bsel * (kMaxT * 32);
+        fr.cx = cx; fr.cy = cy; fr.cz = cz; fr.cs = cs; fr.bsel = bsel;
+        fr.wmax = -1.f;   // statistics are picked up later (pick_stats)
+    };
+    auto build_rows = [&](int nt, const Frame &fr, int k0, int k1, int tt, int tn, float &wmax, int &bad) {
+        const float *rx = sraw + (fr.bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
+        unsigned char *sBb = smem + kOffB + fr.bsel * (kMaxT * 32);
 #pragma unroll 2
-        for (int k = tt; k < npad; k += tn) {
+        for (int k = k0 + tt; k < k1; k += tn) {
             uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
             if (k < nt) {
-                const float x = (rx[k] - cx) * cs, y = (ry[k] - cy) * cs, z = (rz[k] - cz) * cs;
+                const float x = (rx[k] - fr.cx) * fr.cs, y = (ry[k] - fr.cy) * fr.cs, z = (rz[k] - fr.cz) * fr.cs;
                 const float w = __fmaf_rn(z, z, __fmaf_rn(x, x, y * y));
                 bad |= !(w < 4.0f);
                 wmax = fmaxf(wmax, w);
-                unsigned short xh, xl, yh, yl, zh, zl;
-                split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
-                const __half hw1 = __float2half_rn(w);
-                const float wr = w - __half2float(hw1);
-                const __half hw2 = __float2half_rn(wr);
-                const __half hw3 = __float2half_rn(wr - __half2float(hw2));
+                unsigned short xh, xl, yh, yl, zh, zl, w1, w2;
+                split_h2(x, y, xh, xl, yh, yl);
+                split_h2(z, w, zh, zl, w1, w2);          // |t'|^2 = w1 + w2 + w3: the first two terms are w's own (hi, lo)
+                const float wr2 = (w - __half2float(__ushort_as_half(w1))) - __half2float(__ushort_as_half(w2));
+                const unsigned short w3 = __half_as_ushort(__float2half_rn(wr2));
                 v0 = make_uint4(pack2(xh, xl), pack2(xh, yh), pack2(yl, yh), pack2(zh, zl));
-                v1 = make_uint4(pack2(zh, __half_as_ushort(hw1)), pack2(__half_as_ushort(hw2), __half_as_ushort(hw3)), 0u, 0u);
+                v1 = make_uint4(pack2(zh, w1), pack2(w2, w3), 0u, 0u);
             } else {
                 v1.x = pack2(0, __half_as_ushort(__float2half_rn(kPadW)));
             }
@@ -426,14 +454,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             *reinterpret_cast<uint4 *>(dst) = v0;
             *reinterpret_cast<uint4 *>(dst + 128) = v1;
         }
+    };
+    auto publish_stats = [&](int tw, float wmax, int bad) {   // per-warp statistics for pick_stats (after the team's next barrier)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
             bad |= __shfl_xor_sync(0xffffffffu, bad, o);
         }
         if (lane == 0) { s_wstat[tw] = wmax; s_bstat[tw] = bad; }
-        fr.cx = cx; fr.cy = cy; fr.cz = cz; fr.cs = cs; fr.bsel = bsel;
-        fr.wmax = -1.f;   // statistics are picked up after the team's next barrier
+    };
+    // whole operand by one team (steady state: the helpers)
+    auto build_b = [&](int nt, int bsel, int tt, int tn, int tw, auto &&team_bar, Frame &fr) {
+        int bad = 0;
+        float wmax = 0.f;
+        frame_of(nt, bsel, tt, tn, tw, team_bar, fr, bad);
+        build_rows(nt, fr, 0, ((nt + kTileN - 1) / kTileN) * kTileN, tt, tn, wmax, bad);
+        publish_stats(tw, wmax, bad);
     };
     auto pick_stats = [&](int nwarps, Frame &fr) {
         float wmax = 0.f;
@@ -442,7 +478,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         fr.wmax = wmax; fr.bad = bad;
     };
 
-    // ---------------- prologue: the B operand of the first unit is built by the WHOLE CTA (everybody is idle anyway)
+    // ---------------- prologue: the B operand of the first unit is built by the WHOLE CTA (everybody is idle anyway).
+    // (Building it tile by tile behind the scan -- helpers produce 256 rows, signal, the MMA thread and the scanners start -- was
+    // measured slower, 36.9 vs 35.5 us: a tile by 224 threads with its own proxy fence + barrier + arrive costs ~1.1 k cycles,
+    // more than the scan of a tile, so the first unit ran at the producers' pace.)
     Frame fr0 = {0.f, 0.f, 0.f, 1.f, 0.f, 0, 0};
     int group0 = -1;
     float pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;   // helpers, threads < 128: raw query of the unit being staged, loaded early
@@ -462,8 +501,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const float *qp = D.q + (long long)u.cloud * D.q_bs + j * D.q_ps;
             pq1 = __ldg(qp); pq2 = __ldg(qp + D.q_cs); pq3 = __ldg(qp + 2 * D.q_cs);
         }
+        if (tid == 0) stamp(6);
         cp_async_wait_all();
         __syncthreads();
+        if (tid == 0) stamp(7);
         build_b(u.nt, 0, tid, kThreadsTC, warp, [] { __syncthreads(); }, fr0);
         fence_async_smem();
         __syncthreads();
@@ -472,7 +513,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     }
     if (tid == 0) stamp(5);
 
+    // Register budget (24 warps x 80 at launch = 61 440): the scanners need their 64 landing registers and little else, the
+    // helpers' resolve wants more than 80 -- 16 x 32 x 72 + 8 x 32 x 96 = 61 440.  Whole warpgroups (4 consecutive warps)
+    // change together: 0-15 scanners, 16-23 MMA issuer + helpers; everybody returns to 80 before the common tail.
     if (warp < kScanWarps) {
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ================================================= scanners
         const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column group of every tile
         const int row = r * 32 + lane;
@@ -500,24 +545,30 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 const int gg = g0 + t;
                 const int b = gg & (kBufs - 1);
                 const long long w0 = DBG ? clock64() : 0;
-                mbar_wait(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
+                mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
                 if (DBG) a59 += clock64() - w0;
                 tc_fence_after();
                 const int col0 = c * kGroupCols;                       // first column of this warp's share of the tile
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN + col0);
                 const int cid0 = (t * kTileN + col0) / kCh;            // chunk id of the first 32 columns
                 uint32_t ra[32], rb[32];
-                tmem_ld64_wait(ta, ra, rb);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * b);
-                if (DBG && dbg) {
-                    float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                for (int l = 0; l < kGroupCols / 64; ++l) {
+                    tmem_ld64_wait(ta + 64 * l, ra, rb);
+                    if (l == kGroupCols / 64 - 1) {
+                        // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                    }
+                    if (DBG && dbg) {
+                        float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64 * l;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                    }
+                    chunk(ra, cid0 + 2 * l);
+                    chunk(rb, cid0 + 2 * l + 1);
                 }
-                chunk(ra, cid0);
-                chunk(rb, cid0 + 1);
             }
             g0 += ntiles;
             {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
@@ -529,7 +580,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             if (tid == 0) stamp(8 + ul * 6);
         }
         if (DBG && pf && tid == 0) pf[59] = a59;
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     } else if (warp == kMmaWarp) {
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // ================================================= MMA issuer: ONE thread runs the whole loop (an elected
         // issue inside a warp-wide loop costs ~270 cycles per tile on B200, a single-thread loop 64: tools/ubench_umma.cu)
         if (lane == 0) {
@@ -563,7 +616,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             if (DBG && pf) { pf[56] = a56; pf[57] = a57; pf[58] = clock64(); pf[61] = a61; pf[62] = a62; }
         }
         __syncwarp();
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     } else {
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // ================================================= helpers
         const int ht = tid - kHelp0, hw = warp - (kScanWarps + 1);
         int st_group = group0, st_bsel = 0;  // cloud/direction of the most recently staged B operand; its buffer
@@ -610,8 +665,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 sqp[ht] = pq1; sqp[kQB + ht] = pq2; sqp[2 * kQB + ht] = pq3;
                 const float sc = -2.0f * fr_st.cs;
                 const float x = (pq1 - fr_st.cx) * sc, y = (pq2 - fr_st.cy) * sc, z = (pq3 - fr_st.cz) * sc;
-                unsigned short xh, xl, yh, yl, zh, zl;
-                split_h(x, xh, xl); split_h(y, yh, yl); split_h(z, zh, zl);
+                unsigned short xh, xl, yh, yl, zh, zl, uh, ul_;
+                split_h2(x, y, xh, xl, yh, yl);
+                split_h2(z, 0.f, zh, zl, uh, ul_);
                 const unsigned short one = 0x3c00;
                 unsigned char *dst = smem + kOffA + (ul & 1) * (kQB * 32) + (ht >> 3) * 256 + (ht & 7) * 16;
                 *reinterpret_cast<uint4 *>(dst) = make_uint4(pack2(xh, xh), pack2(xl, yh), pack2(yh, yl), pack2(zh, zh));
@@ -749,7 +805,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 if (!stage_changes_group(u2) || f0.bsel == f1.bsel) { stage_issue(ul + 2, u2); issued = true; }
             }
             const long long w0 = DBG ? clock64() : 0;
-            mbar_wait(bar_part + 8 * (ul & 1), (ul >> 1) & 1, s_abort);   // scanners parked unit ul; its MMAs are complete
+            mbar_wait_warp(bar_part + 8 * (ul & 1), (ul >> 1) & 1, s_abort);   // scanners parked unit ul; its MMAs are complete
             if (DBG) a60 += clock64() - w0;
             if (ht == 0) stamp(9 + ul * 6);
             resolve(ul, u0, f0);
@@ -775,6 +831,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             if (ht == 0) stamp(11 + ul * 6);
         }
         if (DBG && pf && ht == 0) pf[60] = a60;
+        if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     }
 
     // ---------------- the deferred exact scans of this CTA, by every warp: with few queries (the usual 0-3) each query is

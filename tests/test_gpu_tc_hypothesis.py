@@ -29,7 +29,7 @@ def adversarial_cloud(kind, rng, b, n):
         p[..., 2] = -3.0
     elif kind == "subnormal_scaled":    # extent ~1 but most coordinates within 2^-20 of the centre: lo parts are fp16 subnormals
         p = 2.0 ** -20 * rng.standard_normal((b, n, 3))
-        p[:, :4] = rng.uniform(-1, 1, size=(b, 4, 3))
+        p[:, :min(4, n)] = rng.uniform(-1, 1, size=(b, min(4, n), 3))
     elif kind == "planar_lattice":      # integer lattice in a plane: exact ties everywhere
         p = np.zeros((b, n, 3))
         p[..., :2] = rng.integers(0, 12, size=(b, n, 2))

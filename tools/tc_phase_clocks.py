@@ -38,6 +38,8 @@ P = P[act]
 print(f"B={b} N={n} M={m}: {act.sum()} CTAs")
 t0 = P[:, 0]
 print(f"  setup (barrier init, TMEM alloc)        {np.mean(P[:, 1] - t0):9.0f}")
+print(f"  prologue: first unit's loads issued at   {np.mean(P[:, 6] - t0):9.0f}")
+print(f"  prologue: raw targets landed at          {np.mean(P[:, 7] - t0):9.0f}")
 print(f"  prologue: first B operand built (CTA)   {np.mean(P[:, 5] - t0):9.0f}")
 print(f"  helpers: units 0 and 1 staged at        {np.mean(P[:, 2] - t0):9.0f}")
 prev_scan = P[:, 2].copy()

@@ -196,8 +196,11 @@ def run(ops="ours", steps=10, warmup=3, batch=32, image=224, proj=True, quiet=Fa
         tm.mark("optimizer")
         return total, logs
 
-    for _ in range(warmup):
-        step(Timer())
+    first_loss = None
+    for i in range(warmup):
+        l0, _ = step(Timer())
+        if i == 0:
+            first_loss = float(l0.detach())      # same weights and data for every op set: a parity check of the two op sets
     torch.cuda.synchronize()
 
     def timed(nsteps, sync_grads):
@@ -218,7 +221,7 @@ def run(ops="ours", steps=10, warmup=3, batch=32, image=224, proj=True, quiet=Fa
         per = {}
         for ph_prev, ph in zip(("start",) + phases[:-1], phases):
             per[ph] = sum(t.ev[ph_prev][0].elapsed_time(t.ev[ph][0]) for t in tms) / nsteps
-        return wall * 1e3, per, float(last)
+        return wall * 1e3, per, float(last.detach())
 
     wall_ms, per, loss_v = timed(steps, True)
     wall_nosync_ms = None
@@ -238,7 +241,7 @@ def run(ops="ours", steps=10, warmup=3, batch=32, image=224, proj=True, quiet=Fa
             "params_M": round(nparam / 1e6, 1), "ms_per_step": wall_ms, "samples_per_s": world * batch / (wall_ms * 1e-3),
             "phase_ms": {k: round(v, 3) for k, v in per.items()},
             "hot_path_fwd_share": hot / max(sum(per.values()), 1e-9),
-            "loss": loss_v,
+            "loss_first_step": first_loss, "loss": loss_v,
             "grad_allreduce": None if world == 1 else {
                 "bytes": 4 * nparam, "step_ms_without_allreduce": stats[1], "exposed_ms": wall_ms - stats[1],
                 "note": "DDP gradient all-reduce over NCCL/NVLink; exposed = step time minus the same step under no_sync()"},

@@ -507,15 +507,30 @@ __device__ __forceinline__ GradTerm grad_term(const GradParams &p, long long gid
     return t;
 }
 
+// o[0], o[cs], o[2 cs] += (vx, vy, vz).  For the reference layout (cs == 1: three adjacent floats) the 8-byte aligned pair goes
+// out as ONE vector atomic (red.global.add.v2.f32, sm_90+): two instructions per term instead of three -- the kernel is bound by
+// the atomic issue rate of the SMs (786 k scalar atomics at config 2), not by bandwidth.  Each element is still added atomically.
+__device__ __forceinline__ void atomic_add3(float *o, long long cs, float vx, float vy, float vz) {
+    if (cs == 1) {
+        if ((reinterpret_cast<unsigned long long>(o) & 7ull) == 0ull) {
+            atomicAdd(reinterpret_cast<float2 *>(o), make_float2(vx, vy));
+            atomicAdd(o + 2, vz);
+        } else {
+            atomicAdd(o, vx);
+            atomicAdd(reinterpret_cast<float2 *>(o + 1), make_float2(vy, vz));
+        }
+    } else {
+        atomicAdd(o, vx);
+        atomicAdd(o + cs, vy);
+        atomicAdd(o + 2 * cs, vz);
+    }
+}
+
 // warp-aggregated scatter of one term per lane (inactive lanes carry unique negative targets and zero values)
 template <bool OVERWRITE>
 __device__ __forceinline__ void grad_scatter(const GradParams &p, bool active, const GradTerm &t, int lane) {
     if (!OVERWRITE && active) {
-        float *o = (t.d2 ? p.g2 : p.g1) + t.own;
-        const long long csa = t.d2 ? p.cs2 : p.cs1;
-        atomicAdd(o, t.v[0]);
-        atomicAdd(o + csa, t.v[1]);
-        atomicAdd(o + 2 * csa, t.v[2]);
+        atomic_add3((t.d2 ? p.g2 : p.g1) + t.own, t.d2 ? p.cs2 : p.cs1, t.v[0], t.v[1], t.v[2]);
     }
     // (the direction is warp-uniform only if total1 % 32 == 0, so the direction bit is folded into the match key)
     const unsigned long long mkey = ((unsigned long long)t.tgt << 1) | (unsigned long long)(t.d2 ? 1 : 0);
@@ -533,11 +548,7 @@ __device__ __forceinline__ void grad_scatter(const GradParams &p, bool active, c
         if (rest) { sx += ox; sy += oy; sz += oz; rest &= rest - 1u; }
     }
     if (active && lane == leader) {
-        float *o = (t.d2 ? p.g1 : p.g2) + t.tgt;
-        const long long csb = t.d2 ? p.cs1 : p.cs2;
-        atomicAdd(o, -sx);
-        atomicAdd(o + csb, -sy);
-        atomicAdd(o + 2 * csb, -sz);
+        atomic_add3((t.d2 ? p.g1 : p.g2) + t.tgt, t.d2 ? p.cs1 : p.cs2, -sx, -sy, -sz);
     }
 }
 

@@ -26,8 +26,11 @@ class emdFunction(Function):
         assert n % 1024 == 0
         assert batchsize <= 512
 
-        xyz1 = xyz1.contiguous().float().cuda()
-        xyz2 = xyz2.contiguous().float().cuda()
+        # (the reference's .cuda() moves CUDA tensors to the CURRENT device, emd_module.py:41-42; here a CUDA input stays on
+        # its own device and only host tensors are moved)
+        xyz1 = xyz1.contiguous().float()
+        xyz1 = xyz1 if xyz1.is_cuda else xyz1.cuda()
+        xyz2 = xyz2.contiguous().float().to(xyz1.device)
         dist = torch.empty(batchsize, n, device=xyz1.device, dtype=torch.float32)
         assignment = torch.empty(batchsize, n, device=xyz1.device, dtype=torch.int32)
         rc = emd.forward_fresh(xyz1, xyz2, dist, assignment, eps, iters)

@@ -159,7 +159,9 @@ def run(ops="ours", steps=10, warmup=3, batch=32, image=224, proj=True, quiet=Fa
     g = torch.Generator().manual_seed(77 + rank)
     images = torch.randn(batch, 3, image, image, generator=g).pin_memory()
     points = torch.rand(batch, 1024, 3, generator=g).pin_memory()
-    dist_mat = torch.from_numpy(pkg.proj_loss.grid_dist(64, 64)).float() if proj else None
+    # the [64,64,64,64] pixel-distance matrix of finetune.py:154 lives on the device here (a 67 MB host tensor that is cloned
+    # and incremented every step would stall the host, not measure the path)
+    dist_mat = torch.from_numpy(pkg.proj_loss.grid_dist(64, 64)).float().to(dev) if proj else None
 
     phases = ("h2d", "model_fwd", "chamfer_fwd", "emd_fwd", "proj", "backward", "optimizer")
 

@@ -31,6 +31,21 @@ def _table_from_dist_mat(dist_mat, h, w):
     return dist_mat[0, 0].to(torch.float32).contiguous()
 
 
+class _ForwardOnly(torch.autograd.Function):
+    """Carries the kernel's values into the autograd graph of inputs that require grad, and refuses to be differentiated: the
+    min-distance terms have no backward kernel (the reference only logs them, finetune.py:160-165, from detached clouds), and
+    silently dropping their gradient would be worse than failing."""
+
+    @staticmethod
+    def forward(ctx, values, *inputs):
+        return values.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise NotImplementedError("proj_loss min-distance terms are forward-only in this library (no backward kernel); "
+                                  "detach them or use the reference's dense torch expression if a gradient is needed")
+
+
 def min_dist_terms(pred, gt, dist_mat, mode="as_written"):
     """min_dist, min_dist_inv of proj_loss.py:25-41 for pred, gt [B,H,W]; dist_mat [H,W,H,W] AFTER its `+= 1`."""
     assert mode in ("as_written", "intended")
@@ -46,7 +61,10 @@ def min_dist_terms(pred, gt, dist_mat, mode="as_written"):
         rc = _lib.lib.psd_proj_min_dist(_lib.ptr(p), _lib.ptr(g), _lib.ptr(table), b, h, w, 0 if mode == "as_written" else 1,
                                         _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.stream_of(p))
     _lib.raise_on_cuda_error(rc, "psd_proj_min_dist")
-    return out[0].to(pred.device), out[1].to(pred.device)   # the reference returns tensors on the inputs' device (CPU)
+    a, b_ = out[0].to(pred.device), out[1].to(pred.device)   # the reference returns tensors on the inputs' device (CPU)
+    if torch.is_grad_enabled() and (pred.requires_grad or gt.requires_grad):
+        a, b_ = _ForwardOnly.apply(a, pred, gt), _ForwardOnly.apply(b_, pred, gt)
+    return a, b_
 
 
 def get_loss_proj(pred, gt, device, loss_type='bce', w=1., min_dist_loss=None, dist_mat=None, opt=None, mode="as_written"):

@@ -262,3 +262,19 @@ def test_host_step_with_the_prediction_on_the_device(pkg, oracle, cuda):
         assert abs(float(loss[0]) - want) <= 1e-5 * want
         got = grad.transpose(1, 2).cpu().numpy()
         assert np.abs(got - w1).max() <= 1e-5 * np.abs(w1).max(), rep
+
+
+def test_proj_min_dist_terms_refuse_to_drop_a_gradient(pkg, cuda):
+    """the min-distance terms have no backward kernel.  With inputs that require grad the values are still right and
+    usable for logging, but differentiating THROUGH them raises instead of silently contributing nothing."""
+    g = torch.Generator().manual_seed(2)
+    pred = torch.rand(2, 16, 16, generator=g).to(cuda).requires_grad_(True)
+    gt = (torch.rand(2, 16, 16, generator=g) > 0.5).float().to(cuda)
+    dm = torch.from_numpy(pkg.proj_loss.grid_dist(16, 16)).float()
+    loss, fwd, bwd = pkg.proj_loss.get_loss_proj(pred, gt, cuda, "bce_prob", 1.0, True, dm)
+    want_f, want_b = pkg.proj_loss.min_dist_terms(pred.detach(), gt, dm)
+    assert torch.equal(fwd.detach(), want_f) and torch.equal(bwd.detach(), want_b) and fwd.requires_grad
+    loss.backward()                                    # the BCE term is plain torch and differentiable
+    assert pred.grad is not None
+    with pytest.raises(NotImplementedError):
+        (1e-4 * fwd.mean()).backward()

@@ -56,6 +56,8 @@ def calibrate(b, n, m, gen, name):
     dump, d1, d2, i1, i2 = run_dump(x.to(dev), y.to(dev))
     xn, yn = x.numpy(), y.numpy()
     worst = 0.0
+    worst_budget = 0.0
+    U = 2.0 ** -24
     qb1 = (n + 127) // 128
     qb2 = (m + 127) // 128
     for d, (qs, ts, qb, off) in enumerate(((xn, yn, qb1, 0), (yn, xn, qb2, b * qb1))):
@@ -71,6 +73,10 @@ def calibrate(b, n, m, gen, name):
             qc = (q.astype(np.float64) - c) * sc
             a = (tc * tc).sum(1)[None, :] - 2.0 * qc @ tc.T           # [nq, nt]
             S = (np.sqrt((qc * qc).sum(1)) + np.sqrt((tc * tc).sum(1).max())) ** 2
+            # per-pair error budget of the margin analysis (chamfer_nn_tc.cu, resolve): relative 15u (|u| + |t'|)^2 plus the
+            # absolute fp16-subnormal part 2^-25 (sqrt(3) (2|u| + |t'|) + 1)
+            un, tn = np.sqrt((qc * qc).sum(1))[:, None], np.sqrt((tc * tc).sum(1))[None, :]
+            budget = 15 * U * (un + tn) ** 2 + 2.0 ** -25 * (1.74 * (2 * un + tn) + 1.0)
             for blk in range(qb):
                 rows = dump[(off + cl * qb + blk) * 128:(off + cl * qb + blk + 1) * 128]
                 q0 = blk * 128
@@ -81,10 +87,12 @@ def calibrate(b, n, m, gen, name):
                     print(f"  NaN in dump: dir {d} cloud {cl} block {blk}: {np.isnan(got).sum()} values")
                     return
                 worst = max(worst, err.max())
+                worst_budget = max(worst_budget, (np.abs(got - a[q0:q0 + nq]) / budget[q0:q0 + nq]).max())
     o1, o2, oi1, oi2 = oracle.chamfer_forward(xn, yn, nthreads=8)
     same = (np.array_equal(d1.view(np.uint32), o1.view(np.uint32)) and np.array_equal(d2.view(np.uint32), o2.view(np.uint32))
             and np.array_equal(i1, oi1) and np.array_equal(i2, oi2))
-    print(f"{name:28s} B={b} N={n} M={m}: max filter error = {worst / 2 ** -24:8.2f} u*S   oracle-identical={same}", flush=True)
+    print(f"{name:28s} B={b} N={n} M={m}: max filter error = {worst / 2 ** -24:8.2f} u*S   "
+          f"max error / per-pair budget = {worst_budget:5.3f}   oracle-identical={same}", flush=True)
 
 
 def parity(b, n, m, gen, name):
@@ -123,6 +131,13 @@ def offset(b, n):
     return torch.rand(b, n, 3, generator=G) + 100.0
 
 
+def adversarial(kind):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_tc_hypothesis import adversarial_cloud
+    rng = np.random.default_rng(5)
+    return lambda b, n: torch.from_numpy(adversarial_cloud(kind, rng, b, n))
+
+
 G = torch.Generator().manual_seed(11)
 if __name__ == "__main__":
     calibrate(1, 128, 128, uniform, "uniform tiny")
@@ -130,6 +145,9 @@ if __name__ == "__main__":
     calibrate(2, 2048, 2048, uniform, "uniform config-2 shape")
     calibrate(2, 2048, 2048, clustered, "clustered")
     calibrate(1, 1024, 2048, offset, "offset +100")
+    # the adversarial distributions of tests/test_gpu_tc_hypothesis.py: the error must stay inside the per-pair budget (< 1)
+    for kind in ("mixed_scales", "outlier_cluster", "split_boundary", "constant_axes", "subnormal_scaled", "planar_lattice", "two_far_clusters"):
+        calibrate(1, 700, 1500, adversarial(kind), "adversarial " + kind)
     parity(32, 2048, 2048, uniform, "uniform config 2")
     parity(32, 2048, 2048, clustered, "clustered config 2")
     parity(8, 1000, 257, uniform, "ragged")

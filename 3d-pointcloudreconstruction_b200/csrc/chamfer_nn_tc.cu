@@ -90,6 +90,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+#ifndef PSD_TC_SPIN
+#define PSD_TC_SPIN 0          // A/B builds: bit 0 = the MMA thread busy-polls (test_wait) instead of try_wait, bit 1 = the scanners too
+#endif
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug must not hang the GPU.  After ~10 s (2e10 cycles: far beyond any legitimate wait, also
 // under compute-sanitizer) the kernel traps: the stream gets a sticky launch failure, so the next CUDA call of the
 // wrappers (and torch's next synchronise) raises instead of returning garbage dist / idx.
@@ -109,11 +118,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
 #ifndef PSD_TC_POLL_LANE0
 #define PSD_TC_POLL_LANE0 0
 #endif
+// busy-polling form of mbar_wait (A/B builds)
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity, volatile int *abort_flag) {
+    long long t0 = 0;
+    for (unsigned spins = 1;; ++spins) {
+        if (mbar_test_wait(bar, parity)) return;
+        if ((spins & 1023u) == 0u) {
+            if (*abort_flag) return;
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 20000000000LL) { *abort_flag = 1; __trap(); }
+        }
+    }
+}
 // warp-wide wait: every lane polls, or (A/B build) lane 0 polls and the warp reconverges behind it
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, volatile int *abort_flag) {
     if (PSD_TC_POLL_LANE0) {
         if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, abort_flag);
         __syncwarp();
+    } else if (PSD_TC_SPIN & 2) {
+        mbar_spin(bar, parity, abort_flag);
     } else {
         mbar_wait(bar, parity, abort_flag);
     }
@@ -169,6 +193,27 @@ __device__ __forceinline__ void tmem_ld64_wait(uint32_t taddr, uint32_t (&a)[32]
           "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15]), "=r"(b[16]), "=r"(b[17]), "=r"(b[18]), "=r"(b[19]), "=r"(b[20]), "=r"(b[21]), "=r"(b[22]), "=r"(b[23]), "=r"(b[24]), "=r"(b[25]), "=r"(b[26]), "=r"(b[27]), "=r"(b[28]), "=r"(b[29]), "=r"(b[30]), "=r"(b[31])
         : "r"(taddr), "r"(taddr + 32u)
         : "memory");
+}
+// Software-pipelined form (PSD_TC_PIPE_LD): ONE tcgen05.ld of 32 columns, and the wait as a separate statement, so that the load
+// of the next 32 columns is in flight while the previous 32 are reduced (two 32-register landing zones: the same 64 registers
+// as the combined form).  The landing registers are outputs of the load statement and in/outputs of the wait statement: the
+// compiler has no reason to touch them in between (nothing else is live but the other landing zone and a few scalars; the
+// SASS is checked for moves out of a landing zone between LDTM and the wait, and the GPU tests compare every bit).
+#ifndef PSD_TC_PIPE_LD
+#define PSD_TC_PIPE_LD 0       // measured: 35.8 us against 35.1 us for the combined load + wait (profiles/r2_tc_ab.txt)
+#endif
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&a)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+                 :: "memory");
 }
 // minimum of 32 filter values: 15 FMNMX3 + 1 FMNMX, four independent chains
 __device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
@@ -552,22 +597,45 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN + col0);
                 const int cid0 = (t * kTileN + col0) / kCh;            // chunk id of the first 32 columns
                 uint32_t ra[32], rb[32];
+                if (PSD_TC_PIPE_LD && !(DBG && dbg)) {
+                    // 32 columns at a time, the next load in flight behind the reduction of the previous one
+                    constexpr int kLd = kGroupCols / 32;
+                    tmem_ld32(ta, ra);
+                    tmem_wait_ld(ra);
 #pragma unroll
-                for (int l = 0; l < kGroupCols / 64; ++l) {
-                    tmem_ld64_wait(ta + 64 * l, ra, rb);
-                    if (l == kGroupCols / 64 - 1) {
-                        // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                    for (int l = 0; l < kLd; l += 2) {
+                        tmem_ld32(ta + 32 * (l + 1), rb);
+                        chunk(ra, cid0 + l);
+                        tmem_wait_ld(rb);
+                        if (l + 2 < kLd) {
+                            tmem_ld32(ta + 32 * (l + 2), ra);
+                        } else {
+                            // every column of this warp's share is in registers: hand the TMEM buffer back before the last min work
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                        }
+                        chunk(rb, cid0 + l + 1);
+                        if (l + 2 < kLd) tmem_wait_ld(ra);
                     }
-                    if (DBG && dbg) {
-                        float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64 * l;
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                    for (int l = 0; l < kGroupCols / 64; ++l) {
+                        tmem_ld64_wait(ta + 64 * l, ra, rb);
+                        if (l == kGroupCols / 64 - 1) {
+                            // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                        }
+                        if (DBG && dbg) {
+                            float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64 * l;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                        }
+                        chunk(ra, cid0 + 2 * l);
+                        chunk(rb, cid0 + 2 * l + 1);
                     }
-                    chunk(ra, cid0 + 2 * l);
-                    chunk(rb, cid0 + 2 * l + 1);
                 }
             }
             g0 += ntiles;
@@ -602,7 +670,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 for (int t = 0; t < ntiles; ++t, ++g) {
                     const int b = g & (kBufs - 1);
                     w0 = DBG ? clock64() : 0;
-                    mbar_wait(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
+                    if (PSD_TC_SPIN & 1) mbar_spin(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
+                    else mbar_wait(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
                     if (DBG) a57 += clock64() - w0;
                     tc_fence_after();
                     const long long w1 = DBG ? clock64() : 0;

@@ -14,6 +14,7 @@ from . import proj_loss        # loss/proj_loss.py mirror (get_loss_proj, grid_d
 from . import icp              # utils/icp.py mirror (icp, best_fit_transform, nearest_neighbor) + icp_batch
 from . import projection       # utils/projection.py mirror (cont_proj, apply_kernel)
 from . import utils            # utils/utils.py sampling helpers (farthest_point_sample, index_points)
+from . import loss_            # loss/loss_.py mirror (cd, distChamfer, batch_NN_loss, fscore) on the CUDA op
 from .dist_chamfer_3D import chamfer_3DDist, chamfer_3DFunction
 from .emd_module import emdFunction, emdModule
 from .fscore import fscore, chamfer_fscore_fused
@@ -21,6 +22,6 @@ from .loss import Loss, chamfer_loss_step_host, ChamferLossPipeline
 from .metrics import Metrics
 
 __all__ = [
-    "chamfer_3D", "emd", "proj_loss", "icp", "projection", "utils", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
+    "chamfer_3D", "emd", "proj_loss", "icp", "projection", "utils", "loss_", "chamfer_3DDist", "chamfer_3DFunction", "emdFunction", "emdModule",
     "fscore", "chamfer_fscore_fused", "Loss", "chamfer_loss_step_host", "ChamferLossPipeline", "Metrics",
 ]

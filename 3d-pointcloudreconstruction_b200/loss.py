@@ -157,10 +157,13 @@ class ChamferLossPipeline:
     (psd_chamfer_loss_step_host_ex with sync = 0); depth = 2 still exposes the host latency at config 2
     (tools/e2e_timeline.py)."""
 
-    def __init__(self, device=None, depth=3):
+    def __init__(self, device=None, depth=3, slot_base=0):
+        """slot_base: first of the library's eight workspace slots this pipeline uses (slot_base .. slot_base + depth - 1); two
+        pipelines that are in flight at the same time (two host threads) must use disjoint slots."""
         import collections
-        assert 1 <= depth <= 8
+        assert 1 <= depth and 0 <= slot_base and slot_base + depth <= 8
         self.depth = depth
+        self.slot_base = slot_base
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         with torch.cuda.device(self.dev):
             self.streams = [torch.cuda.Stream() for _ in range(depth)]
@@ -178,7 +181,7 @@ class ChamferLossPipeline:
         with torch.cuda.device(self.dev):
             rc = _lib.lib.psd_chamfer_loss_step_host_ex(
                 ctypes.c_void_p(pred_host.data_ptr()), ctypes.c_void_p(gt_host.data_ptr()), b, n, m,
-                ctypes.c_void_p(self.loss.data_ptr() + 4 * slot), None, None, None, None, slot, 0,
+                ctypes.c_void_p(self.loss.data_ptr() + 4 * slot), None, None, None, None, self.slot_base + slot, 0,
                 ctypes.c_void_p(self.streams[slot].cuda_stream))
         _lib.raise_on_cuda_error(rc, "psd_chamfer_loss_step_host_ex")
         self.pending.append(slot)
@@ -198,7 +201,7 @@ class ChamferLossPipeline:
             rc = _lib.lib.psd_chamfer_loss_step_pred_dev(
                 ctypes.c_void_p(pred_dev.data_ptr()), int(layout1), ctypes.c_void_p(gt_host.data_ptr()), b, n, m,
                 ctypes.c_void_p(self.loss.data_ptr() + 4 * slot),
-                ctypes.c_void_p(grad_pred_dev.data_ptr()) if grad_pred_dev is not None else None, slot, 0,
+                ctypes.c_void_p(grad_pred_dev.data_ptr()) if grad_pred_dev is not None else None, self.slot_base + slot, 0,
                 ctypes.c_void_p(self.streams[slot].cuda_stream))
         if rc != 1:
             raise RuntimeError(f"psd_chamfer_loss_step_pred_dev failed (rc={rc}): {_lib.last_error()}")

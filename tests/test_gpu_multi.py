@@ -109,3 +109,55 @@ def test_query_sharded_over_two_nccl_ranks(cuda):
     for rank in range(2):
         bad = [k for k, v in ret[rank].items() if not v]
         assert not bad, f"rank {rank}: {bad}"
+
+
+def test_two_host_threads_on_their_own_streams(pkg, oracle, cuda):
+    """the library's mutable state (workspaces, the step-graph cache, switches) is behind a mutex / atomic.
+    Two host threads hammer different entry points on their own streams at the same time -- chamfer forward in multi-tile mode
+    (the library-owned merge workspace, keyed by stream), the fused loss with its backward, the pipelined host step (workspace
+    slots + graph cache) and the auction -- and every result must equal the single-threaded one."""
+    import threading
+    xs, ys = make_clouds("uniform", 2, 300, 4500, seed=31)           # multi-tile on the tensor-core kernel
+    xa, ya = make_clouds("uniform", 24, 1024, 1024, seed=32)
+    ea, eb = make_clouds("uniform", 2, 1024, 1024, seed=33)
+    want_s = oracle.chamfer_forward(xs, ys, nthreads=8)
+    want_a = oracle.chamfer_forward(xa, ya, nthreads=8)
+    want_loss = want_a[0].astype(np.float64).mean() + want_a[1].astype(np.float64).mean()
+    wd, wa = oracle.emd_forward(ea, eb, 0.005, 30, nthreads=2)[:2]
+    errors = []
+
+    def worker(tid):
+        try:
+            torch.cuda.set_device(0)
+            st = torch.cuda.Stream()
+            hx, hy = torch.from_numpy(xa).pin_memory(), torch.from_numpy(ya).pin_memory()
+            with torch.cuda.stream(st):
+                txs, tys = torch.from_numpy(xs).to(cuda), torch.from_numpy(ys).to(cuda)
+                txa, tya = torch.from_numpy(xa).to(cuda), torch.from_numpy(ya).to(cuda)
+                tea, teb = torch.from_numpy(ea).to(cuda), torch.from_numpy(eb).to(cuda)
+                pipe = pkg.ChamferLossPipeline(cuda, depth=2, slot_base=2 * tid)     # disjoint workspace slots per thread
+                for rep in range(6):
+                    old = pkg._lib.lib.psd_chamfer_nn_variant(3 if (rep + tid) % 2 else 0)
+                    out = pkg.chamfer_3DDist()(txs, tys)
+                    pkg._lib.lib.psd_chamfer_nn_variant(old)
+                    a = txa.clone().requires_grad_(True)
+                    loss = pkg.Loss().get_chamfer_loss(a, tya)
+                    loss.backward()
+                    dist, ass = pkg.emdModule()(tea, teb, 0.005, 30)
+                    pipe.submit(hx, hy)
+                    host_loss = pipe.result()
+                    st.synchronize()
+                    for got, w in zip(out, want_s):
+                        assert np.array_equal(got.cpu().numpy(), w), "multi-tile forward"
+                    assert abs(float(loss) - want_loss) <= 1e-5 * want_loss and abs(host_loss - want_loss) <= 1e-5 * want_loss
+                    assert np.array_equal(ass.cpu().numpy(), wa) and np.array_equal(dist.cpu().numpy(), wd)
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    pkg._lib.lib.psd_chamfer_nn_variant(0)
+    assert not errors, errors

@@ -129,6 +129,8 @@ def test_golden_vectors(oracle):
     assert files, "no golden vectors committed"
     for f in files:
         z = np.load(os.path.join(GOLDEN, f))
+        if "meta" not in z.files:       # fixtures of the other mirrors (loss_, ...) are checked by their own tests
+            continue
         meta = json.loads(str(z["meta"]))
         if meta["op"] == "chamfer":
             got = oracle.chamfer_forward(z["xyz1"], z["xyz2"])

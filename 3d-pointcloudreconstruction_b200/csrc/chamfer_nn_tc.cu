@@ -405,6 +405,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     // optional phase clocks (tools/tc_phase_clocks.py): 64 slots per CTA
     long long *pf = (DBG && prof) ? prof + (long long)blockIdx.x * 64 : nullptr;
     auto stamp = [&](int slot) { if (DBG && pf && slot < 56) pf[slot] = clock64(); };
+    // timeline of CTA 0 (tools/tc_timeline.py): 8 rows of 64 tiles behind the per-CTA slots -- the prof buffer holds gridDim.x * 64 + 512
+    // entries.  Rows: 0 MMA issued, 1 committed; scanner warp 0: 2 tile seen full, 3 buffer released, 4 reduction done, 6 first pair of
+    // loads about to issue, 7 first pair landed.
+    long long *tl = (DBG && prof && blockIdx.x == 0) ? prof + (long long)gridDim.x * 64 : nullptr;
+    auto tstamp = [&](int rowi, int g) { if (DBG && tl && g < 64) tl[rowi * 64 + g] = clock64(); };
     if (tid == 0) stamp(0);
     zero_fill(p);
 
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 const long long w0 = DBG ? clock64() : 0;
                 mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
                 if (DBG) a59 += clock64() - w0;
+                if (DBG && tid == 0) tstamp(2, gg);
                 tc_fence_after();
                 const int col0 = c * kGroupCols;                       // first column of this warp's share of the tile
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN + col0);
@@ -621,12 +627,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 } else {
 #pragma unroll
                     for (int l = 0; l < kGroupCols / 64; ++l) {
+                        if (DBG && tl && l == 0 && tid == 0) tstamp(6, gg);
                         tmem_ld64_wait(ta + 64 * l, ra, rb);
+                        if (DBG && tl && l == 0 && warp == 0) {   // (the compare makes the stamp wait for the landed registers)
+                            if (ra[0] != 0x7fc00123u && rb[31] != 0x7fc00123u && lane == 0) tstamp(7, gg);
+                        }
                         if (l == kGroupCols / 64 - 1) {
                             // every column of this warp's share is in registers: hand the TMEM buffer back before the remaining min work
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                            if (DBG && tid == 0) tstamp(3, gg);
                         }
                         if (DBG && dbg) {
                             float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + col0 + 64 * l;
@@ -637,6 +648,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                         chunk(rb, cid0 + 2 * l + 1);
                     }
                 }
+                if (DBG && tl && warp == 0) { if (__float_as_uint(best) != 0x7fc00123u && lane == 0) tstamp(4, gg); }
             }
             g0 += ntiles;
             {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
@@ -675,10 +687,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     if (DBG) a57 += clock64() - w0;
                     tc_fence_after();
                     const long long w1 = DBG ? clock64() : 0;
+                    if (DBG && tl && g < 64) tl[g] = w1;
                     umma_f16(tmem_base + (uint32_t)(b * kTileN), adesc, bdesc, 0u);
                     const long long w2 = DBG ? clock64() : 0;
                     umma_commit(bar_full + 8 * b);
-                    if (DBG) { const long long w3 = clock64(); a61 += w2 - w1; a62 += w3 - w2; }
+                    if (DBG) { const long long w3 = clock64(); a61 += w2 - w1; a62 += w3 - w2; if (tl && g < 64) tl[64 + g] = w3; }
                     bdesc += (uint64_t)((kTileN * 32) >> 4);   // next 128 targets: start-address field, 16-byte units
                 }
             }
@@ -799,6 +812,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const bool ok = live && !fr.bad && (qn < kQMax) && (b2 > b1 + margin);
             float ws = 0.f;   // fused epilogue accumulators of this lane
             int wc = 0;
+            if (DBG && ht == 0) stamp(12 + ul * 6);
             // ---- B
 #pragma unroll
             for (int it = 0; it < (kQW * 4 + 31) / 32; ++it) {
@@ -842,6 +856,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     wc += dbest < p.fs_thr ? 1 : 0;
                 }
             }
+            if (DBG && ht == 0) stamp(13 + ul * 6);
             // ---- C: the exact full scan of a query that failed the margin test is deferred to the end of the kernel
             if (live && !ok) fb_list[atomicAdd(s_nfb, 1)] = (ul << 8) | ql | (fr.bad ? (1 << 30) : 0);
             if ((p.sums != nullptr || p.fs_count != nullptr) && D.ws == nullptr) {   // fused epilogues, one atomic per warp

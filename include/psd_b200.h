@@ -283,7 +283,8 @@ int psd_debug_tc_filter(const float *xyz1, const float *xyz2, int b, int n, int 
                         int *idx2, float *dump, int dump_ld, void *stream);
 
 /* Phase clocks of the tensor-core kernel (tools/tc_phase_clocks.py): while prof_dev is non-NULL every launch of that
- * kernel runs its instrumented build and writes 64 clock64 slots per CTA to prof_dev[148*64].  NULL switches it off. */
+ * kernel runs its instrumented build and writes 64 clock64 slots per CTA to prof_dev[148*64], and CTA 0 its per-tile
+ * timeline (tools/tc_timeline.py) to the 512 entries behind them: prof_dev holds 148*64 + 512 values.  NULL switches it off. */
 int psd_debug_tc_prof(long long *prof_dev);
 
 #ifdef __cplusplus

@@ -25,14 +25,14 @@ y = torch.rand(b, m, 3, generator=g).to(dev)
 out = (torch.empty(b, n, device=dev), torch.empty(b, m, device=dev),
        torch.empty(b, n, device=dev, dtype=torch.int32), torch.empty(b, m, device=dev, dtype=torch.int32))
 L.psd_chamfer_nn_variant(3)
-prof = torch.zeros(148 * 64, dtype=torch.int64, device=dev)
+prof = torch.zeros(148 * 64 + 512, dtype=torch.int64, device=dev)
 L.psd_debug_tc_prof(ctypes.c_void_p(prof.data_ptr()))
 for _ in range(5):
     prof.zero_()
     assert pkg.chamfer_3D.forward(x, y, *out) == 1
 torch.cuda.synchronize()
 L.psd_debug_tc_prof(None)
-P = prof.cpu().numpy().reshape(148, 64).astype(np.float64)
+P = prof.cpu().numpy()[:148 * 64].reshape(148, 64).astype(np.float64)
 act = P[:, 0] > 0
 P = P[act]
 print(f"B={b} N={n} M={m}: {act.sum()} CTAs")
@@ -49,8 +49,9 @@ for u in range(8):
     if not have.any():
         break
     sc, pw, rs, st = P[have, base], P[have, base + 1], P[have, base + 2], P[have, base + 3]
+    ra, rb = P[have, base + 4], P[have, base + 5]
     print(f"  unit {u} ({have.sum():3d} CTAs): scanners done at {np.mean(sc - t0[have]):8.0f} (+{np.mean(sc - prev_scan[have]):6.0f})   "
-          f"helpers: partials seen {np.mean(pw - t0[have]):8.0f}, resolve +{np.mean(rs - pw):6.0f}, next staged +{np.mean(st - rs):6.0f}")
+          f"helpers: partials seen {np.mean(pw - t0[have]):8.0f}, resolve +{np.mean(rs - pw):6.0f} (A {np.mean(ra - pw):5.0f} B {np.mean(rb - ra):5.0f} C {np.mean(rs - rb):5.0f}), next staged +{np.mean(st - rs):6.0f}")
     prev_scan[have] = sc
 print(f"  all roles done (before deferred scans)  {np.mean(P[:, 3] - t0):9.0f}")
 print(f"  deferred exact scans                    {np.mean(P[:, 4] - P[:, 3]):9.0f}")

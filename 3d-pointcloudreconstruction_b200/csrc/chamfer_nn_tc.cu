@@ -41,6 +41,12 @@ namespace tc {
 #ifndef PSD_TC_SETMAXNREG
 #define PSD_TC_SETMAXNREG (PSD_TC_SCAN_WARPS == 16)
 #endif
+#ifndef PSD_TC_ALT_UNROLL
+#define PSD_TC_ALT_UNROLL 2
+#endif
+#ifndef PSD_TC_SCAN_ALT
+#define PSD_TC_SCAN_ALT 1      // scanner warp (r, c) takes ALL 256 columns of the tiles of TMEM buffer c (the two warps of a
+#endif                         // sub-partition work half a period apart instead of sharing every tile in lock-step)
 constexpr int kScanWarps = PSD_TC_SCAN_WARPS;   // warp w reads TMEM lanes 32*(w%4).., column group w/4 of every tile
 constexpr int kMmaWarp = kScanWarps;            // warp index of the MMA issuer
 constexpr int kHelpWarps = 7;                   // 24 (16) warps in all, 80 (128) registers per thread at launch
@@ -48,12 +54,17 @@ constexpr int kHelpThreads = kHelpWarps * 32;
 constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
 constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 768
 constexpr int kColGroups = kScanWarps / 4;      // column groups of a tile (one scanner warp per lane quarter and group)
-constexpr int kTileN = 256;                     // targets per MMA tile = TMEM buffer width (columns)
+#ifndef PSD_TC_TILE_N
+#define PSD_TC_TILE_N 256
+#endif
+constexpr int kAltUnroll = PSD_TC_ALT_UNROLL;
+constexpr int kTileN = PSD_TC_TILE_N;           // targets per MMA tile = TMEM buffer width (columns): 256, or 128 (four buffers) in A/B builds
 constexpr int kBufs = 512 / kTileN;             // TMEM buffers: all 512 columns.  Two 256-column tiles beat four 128-column
                                                 // ones (37.4 vs 41.5 us at B=32, N=M=2048): the mbarrier / tcgen05.commit round
                                                 // trip per tile (~300-400 cycles, tools/ubench_pipe.cu) is paid half as often
-constexpr int kBufShift = 1;                    // log2(kBufs)
-constexpr int kGroupCols = kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
+constexpr int kBufShift = kBufs == 4 ? 2 : 1;   // log2(kBufs)
+static_assert(kTileN == 256 || (kTileN == 128 && PSD_TC_SCAN_ALT), "tile width");
+constexpr int kGroupCols = PSD_TC_SCAN_ALT ? kTileN : kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
 constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     zero_fill(p);
 
     if (tid == 0) {
-        for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, kScanWarps); }
+        for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, PSD_TC_SCAN_ALT ? 4 : kScanWarps); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_ready + 8 * i, 1); mbar_init(bar_part + 8 * i, kScanWarps); }
         *s_abort = 0;
         *s_nfb = 0;
@@ -591,6 +602,34 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             // tile; the TMEM buffer is handed back as soon as they have landed, before any of the min work, so the MMA of tile
             // t + 2 overlaps the reduction of tile t.  Four scanner warps per sub-partition hide the TMEM load latency and the
             // mbarrier round trip behind each other's min work (tools/ubench_pipe.cu: 400 cycles per tile in this form).
+#if PSD_TC_SCAN_ALT
+            static_assert(kScanWarps == 8, "alternating scanners: two warps per sub-partition, warp c takes the tiles that are c mod 2");
+            for (int t = (g0 ^ c) & 1; t < ntiles; t += 2) {
+                const int gg = g0 + t;
+                const int b = gg & (kBufs - 1);
+                mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
+                tc_fence_after();
+                const uint32_t ta = tlane + (uint32_t)(b * kTileN);
+                const int cid0 = (t * kTileN) / kCh;
+                uint32_t ra[32], rb[32];
+#pragma unroll kAltUnroll
+                for (int l = 0; l < kTileN / 64; ++l) {   // rolled: unrolled, ptxas hoists all eight loads and spills the landing zones
+                    tmem_ld64_wait(ta + 64 * l, ra, rb);
+                    if (l == kTileN / 64 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                    }
+                    if (DBG && dbg) {
+                        float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64 * l;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { o[i] = __uint_as_float(ra[i]); o[32 + i] = __uint_as_float(rb[i]); }
+                    }
+                    chunk(ra, cid0 + 2 * l);
+                    chunk(rb, cid0 + 2 * l + 1);
+                }
+            }
+#else
             for (int t = 0; t < ntiles; ++t) {
                 const int gg = g0 + t;
                 const int b = gg & (kBufs - 1);
@@ -650,6 +689,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 }
                 if (DBG && tl && warp == 0) { if (__float_as_uint(best) != 0x7fc00123u && lane == 0) tstamp(4, gg); }
             }
+#endif
             g0 += ntiles;
             {   // park this warp's partial results (double-buffered by unit parity) and tell the helpers
                 float *pp = part + ((ul & 1) * kColGroups + c) * 3 * kQB;

@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     long long *pf = (DBG && prof) ? prof + (long long)blockIdx.x * 64 : nullptr;
     auto stamp = [&](int slot) { if (DBG && pf && slot < 56) pf[slot] = clock64(); };
     // timeline of CTA 0 (tools/tc_timeline.py): 8 rows of 64 tiles behind the per-CTA slots -- the prof buffer holds gridDim.x * 64 + 512
-    // entries.  Rows: 0 MMA issued, 1 committed; scanner warp 0: 2 tile seen full, 3 buffer released, 4 reduction done, 6 first pair of
-    // loads about to issue, 7 first pair landed.
+    // entries.  Rows: 0 MMA issued, 1 committed; scanner warp 0 (even tiles): 2 tile seen full, 3 buffer released, 4 reduction done;
+    // scanner warp 4 (odd tiles): 5, 6, 7 the same (lock-step build: warp 0 only, 6 / 7 = first pair of loads issued / landed).
     long long *tl = (DBG && prof && blockIdx.x == 0) ? prof + (long long)gridDim.x * 64 : nullptr;
     auto tstamp = [&](int rowi, int g) { if (DBG && tl && g < 64) tl[rowi * 64 + g] = clock64(); };
     if (tid == 0) stamp(0);
@@ -607,7 +607,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             for (int t = (g0 ^ c) & 1; t < ntiles; t += 2) {
                 const int gg = g0 + t;
                 const int b = gg & (kBufs - 1);
+                const long long w0 = DBG ? clock64() : 0;
                 mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
+                if (DBG) a59 += clock64() - w0;
+                if (DBG && r == 0 && lane == 0) tstamp(2 + 3 * c, gg);
                 tc_fence_after();
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN);
                 const int cid0 = (t * kTileN) / kCh;
@@ -619,6 +622,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                        if (DBG && r == 0 && lane == 0) tstamp(3 + 3 * c, gg);
                     }
                     if (DBG && dbg) {
                         float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64 * l;
@@ -628,6 +632,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     chunk(ra, cid0 + 2 * l);
                     chunk(rb, cid0 + 2 * l + 1);
                 }
+                if (DBG && tl && r == 0) { if (__float_as_uint(best) != 0x7fc00123u && lane == 0) tstamp(4 + 3 * c, gg); }
             }
 #else
             for (int t = 0; t < ntiles; ++t) {

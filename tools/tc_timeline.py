@@ -30,7 +30,7 @@ L.psd_debug_tc_prof(None)
 P = prof.cpu().numpy()
 t0 = P[0]
 T = P[148 * 64:].reshape(8, 64).astype(np.int64)
-names = ["mma", "commit", "w0 full", "w0 rel", "w0 done", "-", "w0 ld>", "w0 ld<"]
+names = ["mma", "commit", "w0 full", "w0 rel", "w0 done", "w4 full", "w4 rel", "w4 done"]
 print("tile  " + "  ".join(f"{s:>8s}" for s in names) + "   d(mma)")
 prev = None
 for gi in range(64):

@@ -49,7 +49,10 @@ namespace tc {
 #endif                         // sub-partition work half a period apart instead of sharing every tile in lock-step)
 constexpr int kScanWarps = PSD_TC_SCAN_WARPS;   // warp w reads TMEM lanes 32*(w%4).., column group w/4 of every tile
 constexpr int kMmaWarp = kScanWarps;            // warp index of the MMA issuer
-constexpr int kHelpWarps = 7;                   // 24 (16) warps in all, 80 (128) registers per thread at launch
+#ifndef PSD_TC_HELP_WARPS
+#define PSD_TC_HELP_WARPS 7
+#endif
+constexpr int kHelpWarps = PSD_TC_HELP_WARPS;                   // 24 (16) warps in all, 80 (128) registers per thread at launch
 constexpr int kHelpThreads = kHelpWarps * 32;
 constexpr int kHelp0 = (kScanWarps + 1) * 32;   // first helper thread
 constexpr int kThreadsTC = (kScanWarps + 1 + kHelpWarps) * 32;   // 768

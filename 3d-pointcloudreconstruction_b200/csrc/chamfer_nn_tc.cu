@@ -16,9 +16,12 @@
 //
 // One persistent CTA per SM, three concurrent roles (no CTA-wide barrier in the steady state):
 //   * warps 0-7   SCANNERS: warp w reads TMEM lanes 32*(w%4).. (one thread = one query row, so the running minimum
-//                 needs no cross-lane traffic), columns 128*(w/4).. of every tile with tcgen05.ld.32x32b.x32, 64
-//                 columns at a time, and keeps per 32-target chunk (best chunk minimum, its chunk id, second best): 16 min
-//                 instructions + 6 ALU ops per 32 pairs instead of 96 FFMA + 16 FMNMX3 in the FFMA kernel.
+//                 needs no cross-lane traffic) with tcgen05.ld.32x32b.x32, 64 columns at a time, and keeps per 32-target
+//                 chunk (best chunk minimum, its chunk id, second best): 16 min instructions + 6 ALU ops per 32 pairs
+//                 instead of 96 FFMA + 16 FMNMX3 in the FFMA kernel.  ALTERNATING (PSD_TC_SCAN_ALT, default): warp w takes
+//                 all 256 columns of the tiles of TMEM buffer w/4, i.e. every other tile, so that the two warps of a
+//                 sub-partition work half a period apart; the A/B build PSD_TC_SCAN_ALT=0 is the lock-step form (columns
+//                 128*(w/4).. of EVERY tile: both warps wait, load and reduce at the same time) -- 35.0 vs 33.0 us.
 //   * warp  8     MMA issuer: waits for operands (ready mbarrier) and a free TMEM buffer (empty mbarrier), issues one
 //                 tcgen05.mma per tile and commits it to the buffer's full mbarrier.
 //   * warps 9-15  HELPERS: stage the operands two units ahead (raw coordinates -> scaled split fp16, K-major core

@@ -68,8 +68,12 @@ constexpr int kTileN = PSD_TC_TILE_N;           // targets per MMA tile = TMEM b
 constexpr int kBufs = 512 / kTileN;             // TMEM buffers: all 512 columns.  Two 256-column tiles beat four 128-column
                                                 // ones (37.4 vs 41.5 us at B=32, N=M=2048): the mbarrier / tcgen05.commit round
                                                 // trip per tile (~300-400 cycles, tools/ubench_pipe.cu) is paid half as often
-constexpr int kBufShift = kBufs == 4 ? 2 : 1;   // log2(kBufs)
-static_assert(kTileN == 256 || (kTileN == 128 && PSD_TC_SCAN_ALT), "tile width");
+static_assert(kTileN == 256 || ((kTileN == 128 || kTileN == 160) && PSD_TC_SCAN_ALT), "tile width");
+// TMEM buffer and mbarrier phase of the g-th tile of a CTA's stream (kBufs = 2 or 4: masks; 3 buffers of 160 columns: mul-shift division)
+__device__ __forceinline__ int div3(int g) { return (int)(((unsigned long long)(unsigned)g * 0xAAAAAAABull) >> 33); }
+__device__ __forceinline__ int buf_of(int g) { return kBufs == 3 ? g - 3 * div3(g) : (g & (kBufs - 1)); }
+__device__ __forceinline__ int phase_of(int g) { return kBufs == 3 ? (div3(g) & 1) : ((g >> (kBufs == 4 ? 2 : 1)) & 1); }
+constexpr int kBRows = ((2048 + kTileN - 1) / kTileN) * kTileN;   // rows of a B operand buffer: kMaxT rounded up to whole tiles
 constexpr int kGroupCols = PSD_TC_SCAN_ALT ? kTileN : kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
@@ -78,7 +82,7 @@ constexpr float kQMax = 4096.0f;                // scaled |q-c| above this sends
 
 // shared-memory carve-up (bytes)
 constexpr int kOffB = 0;                                  // [2][kMaxT/8][2][8][16 B]
-constexpr int kOffA = kOffB + 2 * kMaxT * 32;             // [2][16][2][8][16 B]
+constexpr int kOffA = kOffB + 2 * kBRows * 32;            // [2][16][2][8][16 B]
 constexpr int kOffRaw = kOffA + 2 * kQB * 32;             // [2][3][kMaxT] raw target coordinates (SoA), by B buffer
 constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][kColGroups][3][128]
 constexpr int kOffSq = kOffPart + 2 * kColGroups * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     };
     auto build_rows = [&](int nt, const Frame &fr, int k0, int k1, int tt, int tn, float &wmax, int &bad) {
         const float *rx = sraw + (fr.bsel * 3) * kMaxT, *ry = rx + kMaxT, *rz = ry + kMaxT;
-        unsigned char *sBb = smem + kOffB + fr.bsel * (kMaxT * 32);
+        unsigned char *sBb = smem + kOffB + fr.bsel * (kBRows * 32);
 #pragma unroll 2
         for (int k = k0 + tt; k < k1; k += tn) {
             uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
@@ -612,24 +616,27 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             static_assert(kScanWarps == 8, "alternating scanners: two warps per sub-partition, warp c takes the tiles that are c mod 2");
             for (int t = (g0 ^ c) & 1; t < ntiles; t += 2) {
                 const int gg = g0 + t;
-                const int b = gg & (kBufs - 1);
+                const int b = buf_of(gg);
                 const long long w0 = DBG ? clock64() : 0;
-                mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
+                mbar_wait_warp(bar_full + 8 * b, phase_of(gg), s_abort);
                 if (DBG) a59 += clock64() - w0;
                 if (DBG && r == 0 && lane == 0) tstamp(2 + 3 * c, gg);
                 tc_fence_after();
                 const uint32_t ta = tlane + (uint32_t)(b * kTileN);
                 const int cid0 = (t * kTileN) / kCh;
                 uint32_t ra[32], rb[32];
+                constexpr int kPairs = kTileN / 64;
+                constexpr bool kTail32 = (kTileN % 64) == 32;   // 160-column tiles: two pairs of loads + one single
+                auto release = [&]() {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * b);
+                    if (DBG && r == 0 && lane == 0) tstamp(3 + 3 * c, gg);
+                };
 #pragma unroll kAltUnroll
-                for (int l = 0; l < kTileN / 64; ++l) {   // rolled: unrolled, ptxas hoists all eight loads and spills the landing zones
+                for (int l = 0; l < kPairs; ++l) {   // (fully unrolled at 256 columns, ptxas hoists all eight loads and spills the landing zones)
                     tmem_ld64_wait(ta + 64 * l, ra, rb);
-                    if (l == kTileN / 64 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_empty + 8 * b);
-                        if (DBG && r == 0 && lane == 0) tstamp(3 + 3 * c, gg);
-                    }
+                    if (!kTail32 && l == kPairs - 1) release();
                     if (DBG && dbg) {
                         float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64 * l;
 #pragma unroll
@@ -638,14 +645,25 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                     chunk(ra, cid0 + 2 * l);
                     chunk(rb, cid0 + 2 * l + 1);
                 }
+                if (kTail32) {
+                    tmem_ld32(ta + 64 * kPairs, ra);
+                    tmem_wait_ld(ra);
+                    release();
+                    if (DBG && dbg) {
+                        float *o = dbg + ((long long)(blk_begin + ul) * kQB + row) * dbg_ld + t * kTileN + 64 * kPairs;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(ra[i]);
+                    }
+                    chunk(ra, cid0 + 2 * kPairs);
+                }
                 if (DBG && tl && r == 0) { if (__float_as_uint(best) != 0x7fc00123u && lane == 0) tstamp(4 + 3 * c, gg); }
             }
 #else
             for (int t = 0; t < ntiles; ++t) {
                 const int gg = g0 + t;
-                const int b = gg & (kBufs - 1);
+                const int b = buf_of(gg);
                 const long long w0 = DBG ? clock64() : 0;
-                mbar_wait_warp(bar_full + 8 * b, (gg >> kBufShift) & 1, s_abort);
+                mbar_wait_warp(bar_full + 8 * b, phase_of(gg), s_abort);
                 if (DBG) a59 += clock64() - w0;
                 if (DBG && tid == 0) tstamp(2, gg);
                 tc_fence_after();
@@ -729,12 +747,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 if (DBG) a56 += clock64() - w0;
                 tc_fence_after();
                 const uint64_t adesc = umma_desc(sA_addr + (uint32_t)(ul & 1) * (kQB * 32));
-                uint64_t bdesc = umma_desc(sB_addr + (uint32_t)bsel * (kMaxT * 32));
+                uint64_t bdesc = umma_desc(sB_addr + (uint32_t)bsel * (kBRows * 32));
                 for (int t = 0; t < ntiles; ++t, ++g) {
-                    const int b = g & (kBufs - 1);
+                    const int b = buf_of(g);
                     w0 = DBG ? clock64() : 0;
-                    if (PSD_TC_SPIN & 1) mbar_spin(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
-                    else mbar_wait(bar_empty + 8 * b, ((g >> kBufShift) & 1) ^ 1, s_abort);
+                    if (PSD_TC_SPIN & 1) mbar_spin(bar_empty + 8 * b, phase_of(g) ^ 1, s_abort);
+                    else mbar_wait(bar_empty + 8 * b, phase_of(g) ^ 1, s_abort);
                     if (DBG) a57 += clock64() - w0;
                     tc_fence_after();
                     const long long w1 = DBG ? clock64() : 0;

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     if (warp < kScanWarps) {
         if (PSD_TC_SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ================================================= scanners
-        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter, column group of every tile
+        const int r = warp & 3, c = warp >> 2;       // TMEM lane quarter; tile parity (alternating form) / column group of every tile (lock-step)
         const int row = r * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(r * 32) << 16);
         int g0 = 0;
@@ -608,10 +608,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
                 best = fminf(best, m);
                 bchunk = lt ? cid : bchunk;
             };
-            // every scanner warp takes its column group (columns c*64 .. c*64+63) of every 256-column tile: ONE pair of loads per
-            // tile; the TMEM buffer is handed back as soon as they have landed, before any of the min work, so the MMA of tile
-            // t + 2 overlaps the reduction of tile t.  Four scanner warps per sub-partition hide the TMEM load latency and the
-            // mbarrier round trip behind each other's min work (tools/ubench_pipe.cu: 400 cycles per tile in this form).
+            // Alternating form (default): warp (r, c) visits the tiles whose index in the CTA's stream is c mod 2 and reduces all of
+            // their columns, four pairs of loads per visit; the TMEM buffer goes back to the MMA thread as soon as the last pair has
+            // landed.  The two warps of a sub-partition are then about half a period apart -- one reduces while the other loads or
+            // waits for its buffer's next tile -- instead of waiting, loading and reducing at the same time.  Lock-step form
+            // (PSD_TC_SCAN_ALT=0): every warp takes its column group of EVERY tile.
 #if PSD_TC_SCAN_ALT
             static_assert(kScanWarps == 8, "alternating scanners: two warps per sub-partition, warp c takes the tiles that are c mod 2");
             for (int t = (g0 ^ c) & 1; t < ntiles; t += 2) {

@@ -31,6 +31,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef PSD_EMD_RHS_FMA
+#define PSD_EMD_RHS_FMA 1     // pass 2 of the two-pass bound scan: the per-object threshold as one fma (0: the round-2 form, A/B builds)
+#endif
+
 namespace psd {
 
 constexpr int kEmdThreads = 1024;
@@ -284,6 +288,10 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         // pass 2 in the squared domain (no sqrt): v >= g2 needs sqrt(s) <= (3 - g2) - price + delta; delta2 bounds the delta
         // of pass 1 for every object that can pass (d <= |c| + |p| + 1)
         const float c = 3.0f - g2;
+        // rhs_k = (c - p_k) + 2e-6 (4 + |c| + 2 |p_k|) as ONE fma per object: prices are >= 0 (they start at 0 and only rise), so
+        // rhs_k = cA - (1 - 4e-6) p_k with cA = c + 2e-6 (4 + |c|).  The different rounding (a few ulp of O(1) values, < 3e-7)
+        // is far inside the slack, which is twice the bound delta of pass 1 (>= 4e-6 to spare).
+        const float cA = c + 2e-6f * (4.0f + fabsf(c));
         for (int k = 4 * t; k < n; k += 4 * tpb) {
             const float4 xa = ld4<GLOBAL>(ox, sx, k), ya = ld4<GLOBAL>(oy, sy, k), za = ld4<GLOBAL>(oz, sz, k);
             const float4 pk = GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(price + k)) : *reinterpret_cast<const float4 *>(price + k);
@@ -295,7 +303,7 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 sv[i] = sqdist_exact(xs[i] - x1, ys[i] - y1, zs[i] - z1);
-                const float rhs = (c - ps[i]) + 2e-6f * (4.0f + fabsf(c) + 2.0f * fabsf(ps[i]));
+                const float rhs = PSD_EMD_RHS_FMA ? __fmaf_rn(-0.999996f, ps[i], cA) : (c - ps[i]) + 2e-6f * (4.0f + fabsf(c) + 2.0f * fabsf(ps[i]));
                 cs[i] = valid && rhs > 0.f && sv[i] <= rhs * rhs * 1.000001f;
                 any |= cs[i];
             }

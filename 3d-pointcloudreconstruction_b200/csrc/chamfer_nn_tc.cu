@@ -44,6 +44,9 @@ namespace tc {
 #ifndef PSD_TC_SETMAXNREG
 #define PSD_TC_SETMAXNREG (PSD_TC_SCAN_WARPS == 16)
 #endif
+#ifndef PSD_TC_TAIL_FAST
+#define PSD_TC_TAIL_FAST 1     // deferred exact scans at the end of the kernel: one-barrier form when every warp has at most one part of one query
+#endif
 #ifndef PSD_TC_ALT_UNROLL
 #define PSD_TC_ALT_UNROLL 2
 #endif
@@ -998,18 +1001,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
         constexpr int kW = kThreadsTC / 32;
         const int nsplit = nfb * 4 <= kW ? 4 : (nfb * 2 <= kW ? 2 : 1);
         unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(part);   // partial results are dead by now
-        for (int i = tid; i < nfb; i += kThreadsTC) s_keys[i] = ~0ull;
-        __syncthreads();
-        for (int item = warp; item < nfb * nsplit; item += kW) {
-            const int fi = item / nsplit;
-            const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
-            const unsigned long long key = fallback_scan(q, item - fi * nsplit, nsplit, lane);
-            if (lane == 0) atomicMin(s_keys + fi, key);
-        }
-        __syncthreads();
-        for (int fi = tid; fi < nfb; fi += kThreadsTC) {
-            const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
-            fallback_write(p, q, s_keys[fi]);
+        if (PSD_TC_TAIL_FAST && nfb * nsplit <= kW) {
+            // the usual case (at most one part of one query per warp): the warp keeps its query in registers across ONE barrier,
+            // every part writes its own slot (no initialisation, no atomics), and part 0 of a query merges and stores -- one
+            // decode + one round trip for the query's coordinates and one CTA barrier less than the general form below
+            const bool mine = warp < nfb * nsplit;
+            const int fi = warp / nsplit, pt = warp - fi * nsplit;
+            FbQuery q;
+            if (mine) {
+                q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                const unsigned long long key = fallback_scan(q, pt, nsplit, lane);
+                if (lane == 0) s_keys[warp] = key;
+            }
+            __syncthreads();
+            if (mine && pt == 0 && lane == 0) {
+                unsigned long long key = s_keys[warp];
+                for (int i = 1; i < nsplit; ++i) { const unsigned long long o = s_keys[warp + i]; key = o < key ? o : key; }
+                fallback_write(p, q, key);
+            }
+        } else {
+            for (int i = tid; i < nfb; i += kThreadsTC) s_keys[i] = ~0ull;
+            __syncthreads();
+            for (int item = warp; item < nfb * nsplit; item += kW) {
+                const int fi = item / nsplit;
+                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                const unsigned long long key = fallback_scan(q, item - fi * nsplit, nsplit, lane);
+                if (lane == 0) atomicMin(s_keys + fi, key);
+            }
+            __syncthreads();
+            for (int fi = tid; fi < nfb; fi += kThreadsTC) {
+                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                fallback_write(p, q, s_keys[fi]);
+            }
         }
         if (nfb > 0 && tid == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
     }

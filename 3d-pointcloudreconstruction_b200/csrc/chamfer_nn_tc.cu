@@ -91,7 +91,8 @@ constexpr int kOffPart = kOffRaw + 2 * 3 * kMaxT * 4;     // [2][kColGroups][3][
 constexpr int kOffSq = kOffPart + 2 * kColGroups * 3 * kQB * 4;    // [3][3][128] raw queries, by unit mod 3
 constexpr int kFbCap = 512;                               // deferred exact-scan list (entries: unit << 8 | query)
 constexpr int kOffFb = kOffSq + 3 * 3 * kQB * 4;
-constexpr int kOffStat = kOffFb + kFbCap * 4;             // [32] wmax, [32] bad, [32] cmax (one per warp), [2] group resident in sraw[i]
+constexpr int kOffFq = kOffFb + kFbCap * 4;                // [3][kFbCap] raw coordinates of the deferred queries
+constexpr int kOffStat = kOffFq + 3 * kFbCap * 4;             // [32] wmax, [32] bad, [32] cmax (one per warp), [2] group resident in sraw[i]
 constexpr int kOffBar = kOffStat + 3 * 32 * 4 + 16;       // 8 mbarriers (8-byte aligned)
 constexpr int kOffMisc = kOffBar + 16 * 8;                // tmem base, nfb, abort
 constexpr int kSmemTC = kOffMisc + 64;
@@ -313,14 +314,14 @@ struct FbQuery {
     const float *bx, *by, *bz;   // generic view of the targets: component base pointers and point stride
     long long ps;
 };
-__device__ __forceinline__ FbQuery fallback_query(const NNParams &p, int blk_begin, int e, const float *sraw, const int *s_rawgroup) {
+__device__ __forceinline__ FbQuery fallback_query(const NNParams &p, int blk_begin, int e, const float *sraw, const int *s_rawgroup,
+                                                  const float *fq) {   // fq: the query's coordinates in the list (x, y, z kFbCap apart)
     FbQuery q;
     q.u = decode_unit(p, blk_begin + ((e & 0x3fffffff) >> 8));
     const NNDirection &D = p.dir[q.u.d];
     q.nt = q.u.nt;
     q.j = D.q_begin + q.u.qblock * kQB + (e & 0xff);
-    const float *__restrict__ qp = D.q + (long long)q.u.cloud * D.q_bs + q.j * D.q_ps;
-    q.x1 = __ldg(qp); q.y1 = __ldg(qp + D.q_cs); q.z1 = __ldg(qp + 2 * D.q_cs);
+    q.x1 = fq[0]; q.y1 = fq[kFbCap]; q.z1 = fq[2 * kFbCap];   // (kept at resolve time: no global round trip in the tail)
     q.nan_possible = ((e >> 30) & 1) || !(fabsf(q.x1) < 1e18f) || !(fabsf(q.y1) < 1e18f) || !(fabsf(q.z1) < 1e18f);
     const int grp = group_of(p, q.u);
     q.res = s_rawgroup[0] == grp ? 0 : (s_rawgroup[1] == grp ? 1 : -1);
@@ -392,10 +393,10 @@ __device__ __forceinline__ void fallback_write(const NNParams &p, const FbQuery 
     if (p.fs_count && dres < p.fs_thr) atomicAdd(p.fs_count + q.u.cloud * 2 + D.slot, 1);
 }
 // one warp per query (used by the helpers when the list has to be flushed in the middle of the kernel)
-__device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, const int *fb_list, int nfb, int wi, int nw,
+__device__ __forceinline__ void run_fallbacks(const NNParams &p, int blk_begin, const int *fb_list, const float *fb_q, int nfb, int wi, int nw,
                                               int lane, const float *sraw, const int *s_rawgroup) {
     for (int fi = wi; fi < nfb; fi += nw) {
-        const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+        const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup, fb_q + fi);
         const unsigned long long key = fallback_scan(q, 0, 1, lane);
         if (lane == 0) fallback_write(p, q, key);
     }
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     float *part = reinterpret_cast<float *>(smem + kOffPart);
     float *sq = reinterpret_cast<float *>(smem + kOffSq);
     int *fb_list = reinterpret_cast<int *>(smem + kOffFb);
+    float *fb_q = reinterpret_cast<float *>(smem + kOffFq);
     int *s_nfb = reinterpret_cast<int *>(smem + kOffMisc) + 1;
     float *s_wstat = reinterpret_cast<float *>(smem + kOffStat);
     int *s_bstat = reinterpret_cast<int *>(smem + kOffStat) + 32;
@@ -931,7 +933,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             }
             if (DBG && ht == 0) stamp(13 + ul * 6);
             // ---- C: the exact full scan of a query that failed the margin test is deferred to the end of the kernel
-            if (live && !ok) fb_list[atomicAdd(s_nfb, 1)] = (ul << 8) | ql | (fr.bad ? (1 << 30) : 0);
+            if (live && !ok) {
+                const int slot = atomicAdd(s_nfb, 1);
+                fb_list[slot] = (ul << 8) | ql | (fr.bad ? (1 << 30) : 0);
+                fb_q[slot] = x1; fb_q[kFbCap + slot] = y1; fb_q[2 * kFbCap + slot] = z1;
+            }
             if ((p.sums != nullptr || p.fs_count != nullptr) && D.ws == nullptr) {   // fused epilogues, one atomic per warp
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -971,7 +977,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             {   // deferred exact scans: flush when the next unit could overflow the list
                 const int nfb = *s_nfb;
                 if (nfb > kFbCap - kQB) {
-                    run_fallbacks(p, blk_begin, fb_list, nfb, hw, kHelpWarps, lane, sraw, s_rawgroup);
+                    run_fallbacks(p, blk_begin, fb_list, fb_q, nfb, hw, kHelpWarps, lane, sraw, s_rawgroup);
                     if (ht == 0) atomicAdd(&g_fallback_queries_tc, (unsigned long long)nfb);
                     help_bar();
                     if (ht == 0) *s_nfb = 0;
@@ -1009,7 +1015,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             const int fi = warp / nsplit, pt = warp - fi * nsplit;
             FbQuery q;
             if (mine) {
-                q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup, fb_q + fi);
                 const unsigned long long key = fallback_scan(q, pt, nsplit, lane);
                 if (lane == 0) s_keys[warp] = key;
             }
@@ -1024,13 +1030,13 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             __syncthreads();
             for (int item = warp; item < nfb * nsplit; item += kW) {
                 const int fi = item / nsplit;
-                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup, fb_q + fi);
                 const unsigned long long key = fallback_scan(q, item - fi * nsplit, nsplit, lane);
                 if (lane == 0) atomicMin(s_keys + fi, key);
             }
             __syncthreads();
             for (int fi = tid; fi < nfb; fi += kThreadsTC) {
-                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup);
+                const FbQuery q = fallback_query(p, blk_begin, fb_list[fi], sraw, s_rawgroup, fb_q + fi);
                 fallback_write(p, q, s_keys[fi]);
             }
         }

@@ -44,6 +44,9 @@ namespace tc {
 #ifndef PSD_TC_SETMAXNREG
 #define PSD_TC_SETMAXNREG (PSD_TC_SCAN_WARPS == 16)
 #endif
+#ifndef PSD_TC_STAGE_FIRST
+#define PSD_TC_STAGE_FIRST 0   // A/B build: helpers stage the operands of unit ul + 2 BEFORE they resolve unit ul.  The MMA thread's operand waits
+#endif                         // go away (4.7 k -> 2.1 k cycles in CTAs that build a second B operand), the launch time does not move (32.8 vs 32.4 us)
 #ifndef PSD_TC_TAIL_FAST
 #define PSD_TC_TAIL_FAST 1     // deferred exact scans at the end of the kernel: one-barrier form when every warp has at most one part of one query
 #endif
@@ -971,6 +974,14 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             mbar_wait_warp(bar_part + 8 * (ul & 1), (ul >> 1) & 1, s_abort);   // scanners parked unit ul; its MMAs are complete
             if (DBG) a60 += clock64() - w0;
             if (ht == 0) stamp(9 + ul * 6);
+            // (A/B build PSD_TC_STAGE_FIRST) operands first: unit ul's MMAs are complete, so its A buffer is free, and (issued) the
+            // staging touches nothing that resolve(ul) reads.  Staged behind the resolve, the operands of unit ul + 2 arrive ~0.8 k
+            // cycles before the MMA thread needs them -- and ~3.9 k cycles too late whenever the unit starts a new cloud/direction
+            // (B operand build, ~4.7 k cycles): all of the slowest CTAs of a launch are such CTAs (tools/tc_cta_balance.py).  With
+            // the operands first those waits disappear, but the helpers' extra work still ends the CTA later: no gain.
+            bool staged = false;
+            Frame f2 = f1;
+            if (PSD_TC_STAGE_FIRST && stage_next && issued) { stage_finish(ul + 2, u2); f2 = fr_st; staged = true; }
             resolve(ul, u0, f0);
             if (ht == 0) stamp(10 + ul * 6);
             help_bar();   // every helper is done with part/sq/sraw of unit ul before anything is restaged
@@ -986,9 +997,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
             }
             f0 = f1;
             if (stage_next) {
-                if (!issued) stage_issue(ul + 2, u2);
-                stage_finish(ul + 2, u2);
-                f1 = fr_st;
+                if (!staged) {
+                    if (!issued) stage_issue(ul + 2, u2);
+                    stage_finish(ul + 2, u2);
+                    f2 = fr_st;
+                }
+                f1 = f2;
             }
             u0 = u1; u1 = u2;
             if (ht == 0) stamp(11 + ul * 6);

@@ -80,7 +80,7 @@ __device__ __forceinline__ int div3(int g) { return (int)(((unsigned long long)(
 __device__ __forceinline__ int buf_of(int g) { return kBufs == 3 ? g - 3 * div3(g) : (g & (kBufs - 1)); }
 __device__ __forceinline__ int phase_of(int g) { return kBufs == 3 ? (div3(g) & 1) : ((g >> (kBufs == 4 ? 2 : 1)) & 1); }
 constexpr int kBRows = ((2048 + kTileN - 1) / kTileN) * kTileN;   // rows of a B operand buffer: kMaxT rounded up to whole tiles
-constexpr int kGroupCols = PSD_TC_SCAN_ALT ? kTileN : kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
+[[maybe_unused]] constexpr int kGroupCols = PSD_TC_SCAN_ALT ? kTileN : kTileN / kColGroups; // columns per tile and scanner warp: kGroupCols / 64 tmem_ld64_wait each
 constexpr int kCh = 32;                         // targets per filter chunk (one tcgen05.ld.x32)
 constexpr int kMaxT = 2048;                     // targets resident in shared memory (B operand: 32 B per target)
 constexpr float kPadW = 32768.0f;               // padding |t'|^2 (fp16-exact), above every admissible filter value

@@ -35,6 +35,21 @@ namespace cg = cooperative_groups;
 #define PSD_EMD_RHS_FMA 1     // pass 2 of the two-pass bound scan: the per-object threshold as one fma (0: the round-2 form, A/B builds)
 #endif
 
+#ifdef PSD_EMD_PROF
+// Instrumented A/B build (tools/emd_phase_clocks.py): thread 0 of block 0 stamps clock64 at the phase boundaries of every
+// iteration of the cluster-wide loop: [it][0..5] = start, compacted + counts exchanged, bids done, barrier A passed,
+// GetMax + barrier B passed, Assign + barrier C passed; [it][6] = bidders of the cluster, [it][7] = 1 for a grid iteration.
+__device__ long long g_emd_prof[256 * 8];
+extern "C" int psd_debug_emd_prof(long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_emd_prof, sizeof(g_emd_prof)) == cudaSuccess ? 1 : 0;
+}
+#define EMD_STAMP(it_, slot_) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it_) < 256) g_emd_prof[(it_) * 8 + (slot_)] = clock64(); } while (0)
+#define EMD_NOTE(it_, slot_, v_) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it_) < 256) g_emd_prof[(it_) * 8 + (slot_)] = (v_); } while (0)
+#else
+#define EMD_STAMP(it_, slot_) do { } while (0)
+#define EMD_NOTE(it_, slot_, v_) do { } while (0)
+#endif
+
 namespace psd {
 
 constexpr int kEmdThreads = 1024;
@@ -537,6 +552,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
     int solo_from = -1;
     for (int it = 0; it < p.iters; ++it) {
         const bool last = (it == p.iters - 1);
+        EMD_STAMP(it, 0);
         // ---- 1. compact the unassigned points homed here (order is result-neutral, emd_cuda.cu:85-93)
         if (tid == 0) *cnt = 0;
         __syncthreads();
@@ -566,6 +582,8 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
         }
         if (total_u == 0) break;  // uniform across the cluster; later iterations cannot change anything
         const int mine = hi - lo;
+        EMD_STAMP(it, 1);
+        EMD_NOTE(it, 6, total_u);
 
         // ---- 2./3. Bid with the object grid: one warp per bidder.  The warp visits the 3x3x3 block of cells around the
         // bidder, then the next shell, ... every object it meets is evaluated exactly.  After a shell of Chebyshev radius
@@ -744,7 +762,10 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
                 }
             }
         }
+        EMD_STAMP(it, 2);
+        EMD_NOTE(it, 7, grid_now ? 1 : 0);
         cluster.sync();  // [A] all bids and max_increments visible cluster-wide
+        EMD_STAMP(it, 3);
 
         // ---- 4. GetMax (emd_cuda.cu:181-194): lowest bidder index within +-1e-6 (fp64) of the maximum
         for (int a = tid; a < u; a += kEmdThreads) {
@@ -758,6 +779,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
         }
         cluster.sync();  // [B]
+        EMD_STAMP(it, 4);
 
         // ---- 5. Assign (emd_cuda.cu:196-215)
         for (int a = tid; a < u; a += kEmdThreads) {
@@ -785,6 +807,7 @@ __global__ void __launch_bounds__(kEmdThreads, 1) emd_auction_kernel(const EmdPa
             }
         }
         cluster.sync();  // [C]
+        EMD_STAMP(it, 5);
         // The number of unassigned points never grows (a winner takes one point off the list and evicts at most one), so once
         // a cloud is down to a handful of bidders it stays there -- typically for hundreds of iterations at the training
         // setting (eps = 0.05, 3000 iterations).  Those iterations are pure latency in the cluster-wide form (three cluster

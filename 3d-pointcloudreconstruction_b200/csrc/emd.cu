@@ -307,6 +307,7 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
         // rhs_k = cA - (1 - 4e-6) p_k with cA = c + 2e-6 (4 + |c|).  The different rounding (a few ulp of O(1) values, < 3e-7)
         // is far inside the slack, which is twice the bound delta of pass 1 (>= 4e-6 to spare).
         const float cA = c + 2e-6f * (4.0f + fabsf(c));
+        const float cB = cA * 1.0000005f, kB = -0.999996f * 1.0000005f;
         for (int k = 4 * t; k < n; k += 4 * tpb) {
             const float4 xa = ld4<GLOBAL>(ox, sx, k), ya = ld4<GLOBAL>(oy, sy, k), za = ld4<GLOBAL>(oz, sz, k);
             const float4 pk = GLOBAL ? __ldcg(reinterpret_cast<const float4 *>(price + k)) : *reinterpret_cast<const float4 *>(price + k);
@@ -318,8 +319,9 @@ __device__ __forceinline__ Top2 scan_bidder(const float *ox, const float *oy, co
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 sv[i] = sqdist_exact(xs[i] - x1, ys[i] - y1, zs[i] - z1);
-                const float rhs = PSD_EMD_RHS_FMA ? __fmaf_rn(-0.999996f, ps[i], cA) : (c - ps[i]) + 2e-6f * (4.0f + fabsf(c) + 2.0f * fabsf(ps[i]));
-                cs[i] = valid && rhs > 0.f && sv[i] <= rhs * rhs * 1.000001f;
+                // (PSD_EMD_RHS_FMA: the factor 1.000001 of the squared threshold is folded into cB / kB: (1.0000005 rhs)^2 >= 1.000001 rhs^2)
+                const float rhs = PSD_EMD_RHS_FMA ? __fmaf_rn(kB, ps[i], cB) : (c - ps[i]) + 2e-6f * (4.0f + fabsf(c) + 2.0f * fabsf(ps[i]));
+                cs[i] = valid && rhs > 0.f && sv[i] <= (PSD_EMD_RHS_FMA ? rhs * rhs : rhs * rhs * 1.000001f);
                 any |= cs[i];
             }
             if (__any_sync(0xffffffffu, any)) {

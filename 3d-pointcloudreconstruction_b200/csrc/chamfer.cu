@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
         if (active) t = grad_term(p, base + lane);   // the second visit is served by L1 / L2
         grad_scatter<OVERWRITE>(p, active, t, lane);
     }
+    if (MODE == 0) pdl_trigger();
 }
 
 // loss = sum_b sums[b,0] / cnt1 + sum_b sums[b,1] / cnt2 -- the epilogue of Loss.get_chamfer_loss (loss/loss.py:36) on
@@ -658,6 +659,7 @@ cudaError_t psd_launch_chamfer_forward(const float *xyz1, const float *xyz2, int
     if (blocks == 0) return only_zero();
     if (blocks > 0x3fffffffLL) return cudaErrorInvalidConfiguration;
     p.zero_buf = zero_buf; p.zero_floats = zero_floats;
+    p.pdl_trigger = 0;
     p.blocks_dir0 = b * p.dir[0].qblocks;
     p.total_blocks = (int)blocks;
     p.sums = sums; p.fs_count = fs_count; p.fs_thr = fs_thr;
@@ -726,6 +728,9 @@ cudaError_t psd_launch_chamfer_backward(const float *xyz1, const float *xyz2, fl
     const long long blocks = (p.total + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (!overwrite) {
+        // A PLAIN launch: as a programmatic dependent of the forward kernel the 512 small CTAs are placed as the forward's CTAs
+        // exit -- eight per SM on the first SMs to drain, none on the last ones -- and the kernel runs on half of the GPU
+        // (38.9 instead of 38.3 us per step).  It still triggers its own successor (the next forward launch, one CTA per SM).
         chamfer_grad_kernel<0><<<(unsigned int)blocks, 256, 0, stream>>>(p);
         return cudaGetLastError();
     }

@@ -43,6 +43,10 @@ struct NNParams {
     // that a training step needs no separate memset
     float *zero_buf;
     long long zero_floats;
+    // tensor-core kernel: signal near the end of a CTA that the next kernel on the stream may be launched (psd_common.cuh,
+    // PSD_PDL).  Off for launches that share the GPU with other launches (psd_chamfer_tc_ctas): a successor CTA that is resident
+    // and waiting for its predecessor would hold an SM that another stream's launch could use.
+    int pdl_trigger;
 };
 
 // grid-wide zero fill of p.zero_buf, a few stores per thread, issued before anything else in the forward kernels

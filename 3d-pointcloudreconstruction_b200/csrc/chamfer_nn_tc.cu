@@ -440,7 +440,6 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     long long *tl = (DBG && prof && blockIdx.x == 0) ? prof + (long long)gridDim.x * 64 : nullptr;
     auto tstamp = [&](int rowi, int g) { if (DBG && tl && g < 64) tl[rowi * 64 + g] = clock64(); };
     if (tid == 0) stamp(0);
-    zero_fill(p);
 
     if (tid == 0) {
         for (int i = 0; i < kBufs; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, PSD_TC_SCAN_ALT ? 4 : kScanWarps); }
@@ -459,6 +458,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     if (tid == 0) stamp(1);
+    pdl_wait();      // everything above is set-up without global accesses: it overlaps the previous kernel's drain (PSD_PDL)
+    zero_fill(p);
 
     // The B operand of a cloud/direction is built from its raw targets in sraw[bsel] (already landed and visible to the team) in
     // two steps.  frame_of: centre and power-of-two scale (one pass over the targets by a team of tn threads -- tt = index in
@@ -1013,6 +1014,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) chamfer_nn_tc_kernel(const NNPa
 
     // ---------------- the deferred exact scans of this CTA, by every warp: with few queries (the usual 0-3) each query is
     // split over up to four warps whose partial minima meet in a shared-memory atomicMin
+    if (p.pdl_trigger) pdl_trigger();   // the next kernel on the stream may be launched; it waits (pdl_wait) until this grid has completed
     tc_fence_before();
     __syncthreads();
     if (tid == 0) stamp(3);
@@ -1222,9 +1224,10 @@ cudaError_t psd_launch_nn_tc(const NNParams &p_in, DeviceState *ds, cudaStream_t
     int grid = p.total_blocks < ds->num_sms ? p.total_blocks : ds->num_sms;
     const int cap = g_tc_max_ctas.load();
     if (cap > 0 && grid > cap) grid = cap;
-    if (dbg || prof) tc::chamfer_nn_tc_kernel<true><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, dbg, dbg_ld, prof);
-    else tc::chamfer_nn_tc_kernel<false><<<grid, tc::kThreadsTC, tc::kSmemTC, stream>>>(p, nullptr, 0, nullptr);
-    cudaError_t e = cudaGetLastError();
+    p.pdl_trigger = (cap > 0 && grid == cap) ? 0 : 1;
+    cudaError_t e;
+    if (dbg || prof) e = psd_launch_pdl(p.pdl_trigger != 0, tc::chamfer_nn_tc_kernel<true>, dim3(grid), dim3(tc::kThreadsTC), tc::kSmemTC, stream, p, dbg, dbg_ld, prof);
+    else e = psd_launch_pdl(p.pdl_trigger != 0, tc::chamfer_nn_tc_kernel<false>, dim3(grid), dim3(tc::kThreadsTC), tc::kSmemTC, stream, p, (float *)nullptr, 0, (long long *)nullptr);
     if (ws_elems) {
         if (e == cudaSuccess) {
             const long long total = (p.dir[0].ws ? (long long)b * p.dir[0].q_count : 0) + (p.dir[1].ws ? (long long)b * p.dir[1].q_count : 0);

@@ -29,6 +29,21 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// Programmatic dependent launch (PSD_PDL, default on): the library's stream-ordered kernel pairs (NN forward -> gradient -> next
+// forward) are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  A kernel signals near its END that its
+// successor may be launched (pdl_trigger: the successor's launch latency and set-up overlap this kernel's tail and drain) and
+// waits for its predecessor's completion and memory (pdl_wait) before its FIRST global access: same results as plain stream
+// order, whatever the neighbouring kernels are (a predecessor that never triggers does so implicitly when it completes).
+#ifndef PSD_PDL
+#define PSD_PDL 1
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+    if (PSD_PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+    if (PSD_PDL) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned long long pack_key(float d, int idx) {
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)idx;
 }
@@ -38,6 +53,18 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 
 }  // namespace psd
+
+// host side of PSD_PDL: a launch whose kernel calls pdl_wait() before its first global access
+template <typename... KArgs, typename... Args>
+static inline cudaError_t psd_launch_pdl(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = (PSD_PDL && allow) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // host-side error plumbing (psd_capi.cu)
 void psd_set_error(const char *what, cudaError_t err);

@@ -23,6 +23,9 @@
 #include "chamfer_nn.cuh"
 #include "psd_device.h"
 
+#ifndef PSD_GRAD_TRIGGER_EARLY
+#define PSD_GRAD_TRIGGER_EARLY 1
+#endif
 namespace psd {
 
 constexpr int kWarps = 16;        // one persistent CTA per SM: 4 warps on each of the four sub-partitions
@@ -564,6 +567,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
     const long long gid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active0 = gid0 < p.total;
+    if (MODE == 0 && PSD_GRAD_TRIGGER_EARLY) pdl_trigger();   // the next forward launch may be scheduled as the SMs drain (it waits before its first global access)
     GradTerm t0;
     t0.d2 = false; t0.own = 0; t0.tgt = -1 - (long long)lane; t0.v[0] = t0.v[1] = t0.v[2] = 0.f;
     if (active0) t0 = grad_term(p, gid0);
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(256) chamfer_grad_kernel(const GradParams p) {
         if (active) t = grad_term(p, base + lane);   // the second visit is served by L1 / L2
         grad_scatter<OVERWRITE>(p, active, t, lane);
     }
-    if (MODE == 0) pdl_trigger();
+    if (MODE == 0 && !PSD_GRAD_TRIGGER_EARLY) pdl_trigger();
 }
 
 // loss = sum_b sums[b,0] / cnt1 + sum_b sums[b,1] / cnt2 -- the epilogue of Loss.get_chamfer_loss (loss/loss.py:36) on

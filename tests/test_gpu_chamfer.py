@@ -360,3 +360,45 @@ def test_large_cloud_properties(pkg, oracle, cuda):
     # bit-exact slice against the oracle: first 2048 queries of direction 1 against all targets
     wd, _, wi, _ = oracle.chamfer_forward(x[:, :2048].numpy(), y.numpy(), nthreads=16)
     assert np.array_equal(d1[:, :2048].cpu().numpy(), wd) and np.array_equal(out["idx1"][:, :2048].cpu().numpy(), wi)
+
+
+def test_stream_order_with_programmatic_dependent_launch(pkg, oracle, cuda):
+    """The tensor-core forward kernel is launched as a programmatic dependent of whatever precedes it on the stream (PSD_PDL): its
+    set-up may overlap the predecessor's drain, its first global access must not.  (1) inputs PRODUCED by a kernel that was
+    launched right in front of it, no synchronisation in between; (2) back-to-back forward / backward / forward launches on
+    different inputs that REUSE the same output and gradient buffers through the raw entry points.  Everything bit-equal to the
+    oracle, every repetition."""
+    b, n, m = 24, 1024, 1024                      # >= 2 units per SM: the automatic choice takes the tensor-core kernel as well
+    sets = [make_clouds(kind, b, n, m, seed=70 + i) for i, kind in enumerate(("uniform", "clustered", "uniform"))]
+    wants = [oracle.chamfer_forward(x, y, nthreads=8) for x, y in sets]
+    bases = [(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)) for x, y in sets]
+    torch.cuda.synchronize()
+    # (1) producer kernels directly in front of the launch
+    for rep in range(4):
+        for (bx, by), want in zip(bases, wants):
+            tx = bx * 2.0 - bx          # elementwise kernels on the same stream: tx == bx bit for bit, written just now
+            ty = by * 2.0 - by
+            got = pkg.chamfer_3DDist()(tx, ty)
+            assert_bit_equal([g.cpu().numpy() for g in got], want, f"producer in front, repetition {rep}")
+    # (2) raw entry points, shared output buffers, forward -> backward -> forward without synchronisation
+    d1 = torch.empty(b, n, device=cuda); d2 = torch.empty(b, m, device=cuda)
+    i1 = torch.empty(b, n, device=cuda, dtype=torch.int32); i2 = torch.empty(b, m, device=cuda, dtype=torch.int32)
+    g1 = torch.zeros(b, n, 3, device=cuda); g2 = torch.zeros(b, m, 3, device=cuda)
+    gd1 = torch.ones(b, n, device=cuda); gd2 = torch.ones(b, m, device=cuda)
+    snaps = []
+    for rep in range(3):
+        for k, (bx, by) in enumerate(bases):
+            assert pkg.chamfer_3D.forward(bx, by, d1, d2, i1, i2) == 1
+            g1.zero_(); g2.zero_()
+            assert pkg.chamfer_3D.backward(bx, by, g1, g2, gd1, gd2, i1, i2) == 1
+            snaps.append((k, d1.clone(), d2.clone(), i1.clone(), i2.clone(), g1.clone(), g2.clone()))
+    torch.cuda.synchronize()
+    ref_grads = {}
+    for k, sd1, sd2, si1, si2, sg1, sg2 in snaps:
+        assert_bit_equal([sd1.cpu().numpy(), sd2.cpu().numpy(), si1.cpu().numpy(), si2.cpu().numpy()], wants[k], f"back-to-back set {k}")
+        if k not in ref_grads:
+            x, y = sets[k]
+            ref_grads[k] = oracle.chamfer_backward(x, y, np.ones((b, n), np.float32), np.ones((b, m), np.float32), wants[k][2], wants[k][3])
+        for got, want in zip((sg1, sg2), ref_grads[k]):
+            got = got.cpu().numpy()
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-6), f"gradient of set {k}: max abs diff {np.abs(got - want).max()}"

@@ -435,9 +435,9 @@ def main():
     t_sync = wall_ms(lambda: [e2e_step_sync(s) for s in range(200)])
     lib.psd_chamfer_tc_ctas(TC_CTAS)   # DEPTH steps in flight: the launches share the SMs (captured into the step graphs)
     e2e_run_pipelined(W + 2 * DEPTH, False)   # every (buffer, slot) combination seen twice: its CUDA graph is cached
-    t_pipe = statistics.median([wall_ms(lambda: e2e_run_pipelined(Ke, False)) for _ in range(3)])
+    t_pipe = statistics.median([wall_ms(lambda: e2e_run_pipelined(Ke, False)) for _ in range(5)])
     e2e_run_pipelined(W + 2 * DEPTH, True)
-    t_gt = statistics.median([wall_ms(lambda: e2e_run_pipelined(Ke, True)) for _ in range(3)])
+    t_gt = statistics.median([wall_ms(lambda: e2e_run_pipelined(Ke, True)) for _ in range(5)])
     lib.psd_chamfer_tc_ctas(0)
     t_pipe, t_gt, t_sync, t_torch = max_over_ranks([t_pipe, t_gt, t_sync, t_torch])
     e2e_value = world * pairs_step * Ke / (t_pipe * 1e-3)
@@ -457,7 +457,7 @@ def main():
                    "parallelism": f"batch-sharded x{world}, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": 4 * 3 * B * (N + M), "d2h_bytes_per_step": 4,
                 "steps": Ke, "ms_per_step": t_pipe / Ke, "pipeline_depth": DEPTH, "tc_ctas_per_launch": TC_CTAS,
-                "api": "psd_chamfer_loss_step_host_ex (C ABI, pinned host buffers), pipelined: per step H2D of BOTH clouds + chamfer fwd + mean loss [loss/loss.py:36] + bwd + D2H loss; up to 8 steps in flight on 8 streams/workspaces, each replayed from a cached CUDA graph; every step's loss is read on the host; median of 3 runs of `steps` steps, wall clock, max over ranks",
+                "api": "psd_chamfer_loss_step_host_ex (C ABI, pinned host buffers), pipelined: per step H2D of BOTH clouds + chamfer fwd + mean loss [loss/loss.py:36] + bwd + D2H loss; up to 8 steps in flight on 8 streams/workspaces, each replayed from a cached CUDA graph; every step's loss is read on the host; median of 5 runs of `steps` steps, wall clock, max over ranks",
                 "gt_only": {"value": world * pairs_step * Ke / (t_gt * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": 4 * 3 * B * M,
                             "d2h_bytes_per_step": 4, "ms_per_step": t_gt / Ke,
                             "api": "psd_chamfer_loss_step_pred_dev: the training loop's real shape (train.py:160-163) -- the prediction is the generator's [B,3,N] device tensor (read in place), only the ground truth crosses PCIe; d loss / d pred stored in the prediction's layout on the device"},
